@@ -1,0 +1,496 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a.
+//
+// Replaces every F.conv2d / nn.Linear / ConvTranspose2d-phase on the reference hot path
+// (detectron2/layers/wrappers.py:104-112 Conv2d.forward, box_head.py:95-98, chart.py:76-90).
+//
+// GEMM view: M = output pixels (a TMA box of tw x th x tn pixels, <= 128 rows), N = Cout tile
+// (block_n <= 256), K = taps x Cin in 64-channel slabs. Per K-slab the producer issues one 4-D TMA
+// box load of the shifted input window (zero fill outside the image implements the padding) and
+// one 2-D load of the packed weights, both 128B-swizzled; one thread issues four
+// tcgen05.mma (K=16 each) into a TMEM accumulator; four epilogue warps drain TMEM with tcgen05.ld
+// and fuse bias / residual / nearest-x2 top-down add / ReLU / dtype conversion.
+//
+// Warp roles (256 threads, persistent, 1 CTA per SM):
+//   warp 0 lane 0 : TMA producer          warp 1 lane 0 : MMA issuer
+//   warp 2        : TMEM alloc / dealloc  warps 4..7    : epilogue (TMEM lane quarter = warp % 4)
+#include "conv_igemm.cuh"
+#include "ptx.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace dpb {
+
+static thread_local char g_err[512];
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+static constexpr int kThreads = 256;
+static constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ConvKParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // 1024-byte aligned stage buffers (SWIZZLE_128B atoms are 8 rows x 128 B)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
+  const uint32_t stage_bytes = kABytes + ((b_bytes + 1023u) & ~1023u);
+  const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
+  // barriers: full[s], empty[s], tmem_full[2], tmem_empty[2]; then the TMEM base address slot
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(p.stages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (uint32_t)(2 * p.stages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(2 * p.stages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * p.stages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const uint32_t tmem_cols = 2u * (uint32_t)p.acc_stride;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int nvalid = p.n_valid ? min(*p.n_valid, p.N) : p.N;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_tiles = m_tiles * p.n_blocks;
+  const int k_iters = p.kh * p.kw * p.cin_chunks;
+  const uint32_t a_tx = p.im2col ? (uint32_t)kABytes : (uint32_t)(p.tw * p.th * p.tn) * 128u;
+  const int hw_out = p.H_out * p.W_out;
+  const int m_valid = nvalid * hw_out;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_blocks;
+      const int mt = tile / p.n_blocks;
+      int ix0, iy0, in0;
+      if (p.im2col) {
+        // column = 128 consecutive output pixels in (n, oy, ox) order
+        const int m0 = mt * 128;
+        if (m0 >= m_valid) continue;
+        in0 = m0 / hw_out;
+        const int rem = m0 - in0 * hw_out;
+        const int oy0 = rem / p.W_out;
+        ix0 = (rem - oy0 * p.W_out) * p.sx - p.pad_x;
+        iy0 = oy0 * p.sy - p.pad_y;
+      } else {
+        const int twi = mt % p.tiles_w;
+        const int thi = (mt / p.tiles_w) % p.tiles_h;
+        const int tni = mt / (p.tiles_w * p.tiles_h);
+        if (tni * p.tn >= nvalid) continue;
+        ix0 = twi * p.tw * p.sx - p.pad_x;
+        iy0 = thi * p.th * p.sy - p.pad_y;
+        in0 = tni * p.tn;
+      }
+      int kcol = 0;
+      for (int ky = 0; ky < p.kh; ++ky) {
+        for (int kx = 0; kx < p.kw; ++kx) {
+          for (int cc = 0; cc < p.cin_chunks; ++cc) {
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
+            mbar_expect_tx(full_bar(s), a_tx + b_bytes);
+            if (p.im2col)
+              tma_load_im2col_4d(a_dst, &tmA, full_bar(s), cc * 64, ix0, iy0, in0,
+                                 (uint16_t)(kx * p.dil), (uint16_t)(ky * p.dil));
+            else
+              tma_load_4d(a_dst, &tmA, full_bar(s), cc * 64, ix0 + kx * p.dil, iy0 + ky * p.dil,
+                          in0);
+            tma_load_2d(a_dst + kABytes, &tmB, full_bar(s), kcol, n_blk * p.block_n);
+            kcol += 64;
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_bf16(128, p.block_n);
+    int s = 0;
+    uint32_t ph = 0;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_blocks;
+      if (p.im2col) {
+        if (mt * 128 >= m_valid) continue;
+      } else {
+        if ((mt / (p.tiles_w * p.tiles_h)) * p.tn >= nvalid) continue;
+      }
+      mbar_wait(tempty_bar(as), aph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_stride);
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
+        const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32),
+                    idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));  // frees the smem slot when these MMAs retire
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+      if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int rows_in_tile = p.im2col ? 128 : p.tw * p.th * p.tn;
+    const int rx = p.im2col ? 0 : row % p.tw;
+    const int ry = p.im2col ? 0 : (row / p.tw) % p.th;
+    const int rn = p.im2col ? 0 : row / (p.tw * p.th);
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_blocks;
+      const int mt = tile / p.n_blocks;
+      int ox, oy, on;
+      if (p.im2col) {
+        const int m0 = mt * 128;
+        if (m0 >= m_valid) continue;
+        const int m = m0 + row;
+        on = m / hw_out;
+        const int rem = m - on * hw_out;
+        oy = rem / p.W_out;
+        ox = rem - oy * p.W_out;
+      } else {
+        const int twi = mt % p.tiles_w;
+        const int thi = (mt / p.tiles_w) % p.tiles_h;
+        const int tni = mt / (p.tiles_w * p.tiles_h);
+        if (tni * p.tn >= nvalid) continue;
+        ox = twi * p.tw + rx;
+        oy = thi * p.th + ry;
+        on = tni * p.tn + rn;
+      }
+      const bool valid = row < rows_in_tile && ox < p.W_out && oy < p.H_out && on < nvalid;
+      const int c_base = n_blk * p.block_n;
+      const long long out_off = on * p.out_sn + oy * p.out_sy + ox * p.out_sx + c_base;
+      const __nv_bfloat16* res_ptr = nullptr;
+      if (p.res != nullptr && valid) {
+        res_ptr = p.res + on * p.res_sn + (long long)(oy >> p.res_shift) * p.res_sy +
+                  (long long)(ox >> p.res_shift) * p.res_sx + c_base;
+      }
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.acc_stride);
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(t_addr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + c_base + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b = __ldg(b4 + i);
+              f[4 * i + 0] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+            }
+          }
+          if (res_ptr != nullptr) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(res_ptr + c0);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const uint4 r = __ldg(r4 + i);
+              f[8 * i + 0] += bf16_lo(r.x); f[8 * i + 1] += bf16_hi(r.x);
+              f[8 * i + 2] += bf16_lo(r.y); f[8 * i + 3] += bf16_hi(r.y);
+              f[8 * i + 4] += bf16_lo(r.z); f[8 * i + 5] += bf16_hi(r.z);
+              f[8 * i + 6] += bf16_lo(r.w); f[8 * i + 7] += bf16_hi(r.w);
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
+          }
+          if (p.out_fp32) {
+            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          } else {
+            uint4* o4 =
+                reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + c0);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              uint4 o;
+              o.x = pack_bf16(f[8 * i + 0], f[8 * i + 1]);
+              o.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
+              o.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
+              o.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+              o4[i] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+    set_error("cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+int encode_tiled_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr) {
+  PFN_encodeTiled fn = get_encode_tiled();
+  if (!fn) return -1;
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                  dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu,%llu,%llu,%llu box "
+              "%u,%u,%u,%u)",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)(rank > 2 ? dims[2] : 0),
+              (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0,
+              rank > 3 ? box[3] : 0);
+    return -2;
+  }
+  return 0;
+}
+
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                     const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                     cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                     CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_im2col_bf16(CUtensorMap* tm, const void* base, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const int* lower, const int* upper,
+                       uint32_t channels, uint32_t pixels, const uint32_t* estr, int swizzle128) {
+  static PFN_encodeIm2col fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+      set_error("cuTensorMapEncodeIm2col unavailable (%s)", cudaGetErrorString(e));
+      return -1;
+    }
+    fn = reinterpret_cast<PFN_encodeIm2col>(p);
+  }
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
+                  strides_bytes, lower, upper, channels, pixels, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeIm2col failed: CUresult %d (dims %llu,%llu,%llu,%llu strides "
+              "%llu,%llu,%llu lower %d,%d upper %d,%d estr %u,%u)",
+              (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)dims[2], (unsigned long long)dims[3],
+              (unsigned long long)strides_bytes[0], (unsigned long long)strides_bytes[1],
+              (unsigned long long)strides_bytes[2], lower[0], lower[1], upper[0], upper[1], estr[1],
+              estr[2]);
+    return -2;
+  }
+  return 0;
+}
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Pick the (tw, th, tn) pixel box that minimises the number of 128-row MMA tiles.
+static void choose_tile(int W, int H, int N, int sx, int sy, int* tw_o, int* th_o, int* tn_o) {
+  long long best_cost = -1;
+  int btw = 1, bth = 1, btn = 1;
+  const int max_tw = 256 / sx < 128 ? 256 / sx : 128;
+  const int max_th = 256 / sy < 128 ? 256 / sy : 128;
+  for (int tw = 1; tw <= W && tw <= max_tw; ++tw) {
+    for (int th = 1; th <= H && th <= max_th && tw * th <= 128; ++th) {
+      int tn = 1;
+      if (tw == W && th == H) {
+        tn = 128 / (tw * th);
+        if (tn > N) tn = N;
+        if (tn < 1) tn = 1;
+      }
+      long long cost = (long long)ceil_div(W, tw) * ceil_div(H, th) * ceil_div(N, tn);
+      // tie-break: wider boxes (longer contiguous runs)
+      if (best_cost < 0 || cost < best_cost || (cost == best_cost && tw > btw)) {
+        best_cost = cost; btw = tw; bth = th; btn = tn;
+      }
+    }
+  }
+  *tw_o = btw; *th_o = bth; *tn_o = btn;
+}
+
+int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
+  if (!d.x || !d.w || !d.out) { set_error("conv: null pointer"); return -1; }
+  if (d.cin_pad % 64 != 0 || d.cout_pad % 16 != 0) {
+    set_error("conv: cin_pad %d must be a multiple of 64 and cout_pad %d of 16", d.cin_pad,
+              d.cout_pad);
+    return -1;
+  }
+  ConvKParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  // N tile
+  int block_n = d.block_n;
+  if (block_n == 0) {
+    if (d.cout_pad <= 256) block_n = d.cout_pad;
+    else {
+      // largest multiple of 16 that divides cout_pad and is <= 256
+      block_n = 16;
+      for (int b = 256; b >= 16; b -= 16)
+        if (d.cout_pad % b == 0) { block_n = b; break; }
+    }
+  }
+  if (block_n % 16 != 0 || block_n > 256 || d.cout_pad % block_n != 0) {
+    set_error("conv: bad block_n %d for cout_pad %d", block_n, d.cout_pad);
+    return -1;
+  }
+  p.block_n = block_n;
+  p.n_blocks = d.cout_pad / block_n;
+  p.acc_stride = block_n <= 32 ? 32 : block_n <= 64 ? 64 : block_n <= 128 ? 128 : 256;
+  p.im2col = d.im2col;
+  if (d.im2col) {
+    const long long m_total = (long long)d.N * d.H_out * d.W_out;
+    if (m_total >= (1LL << 31) - 128) { set_error("conv: too many output pixels"); return -1; }
+    p.tw = 128; p.th = 1; p.tn = 1;
+    p.tiles_w = (int)((m_total + 127) / 128); p.tiles_h = 1; p.tiles_n = 1;
+  } else {
+    choose_tile(d.W_out, d.H_out, d.N, d.sx, d.sy, &p.tw, &p.th, &p.tn);
+    p.tiles_w = ceil_div(d.W_out, p.tw);
+    p.tiles_h = ceil_div(d.H_out, p.th);
+    p.tiles_n = ceil_div(d.N, p.tn);
+  }
+  p.H_out = d.H_out; p.W_out = d.W_out; p.N = d.N;
+  p.kh = d.kh; p.kw = d.kw; p.sx = d.sx; p.sy = d.sy; p.pad_x = d.pad_x; p.pad_y = d.pad_y;
+  p.dil = d.dil;
+  p.cin_chunks = d.cin_pad / 64;
+  p.relu = d.relu; p.out_fp32 = d.out_fp32; p.res_shift = d.res_shift;
+  p.bias = d.bias;
+  p.res = reinterpret_cast<const __nv_bfloat16*>(d.res);
+  p.res_sn = d.res_sn; p.res_sy = d.res_sy; p.res_sx = d.res_sx;
+  p.out = d.out; p.out_sn = d.out_sn; p.out_sy = d.out_sy; p.out_sx = d.out_sx;
+  p.n_valid = d.n_valid;
+
+  const int b_bytes = (block_n * 128 + 1023) & ~1023;
+  const int stage_bytes = kABytes + b_bytes;
+  int stages = d.stages;
+  if (stages == 0) {
+    stages = (220 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    const int k_iters = d.kh * d.kw * p.cin_chunks;
+    if (stages > k_iters + 1) stages = k_iters + 1;
+    if (stages < 2) stages = 2;
+  }
+  p.stages = stages;
+  plan->smem = stages * stage_bytes + 1024 /*align slack*/ + 8 * (2 * stages + 4) + 16;
+
+  // A: 4-D (C, W, H, N) view of the input; box = (64 ch, tw, th, tn) output pixels, traversal
+  // strides implement the convolution stride.
+  {
+    uint64_t dims[4] = {(uint64_t)d.Cin, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.N};
+    uint64_t strides[3] = {(uint64_t)d.x_sw * 2, (uint64_t)d.x_sh * 2, (uint64_t)d.x_sn * 2};
+    uint32_t box[4] = {64, (uint32_t)(p.tw * d.sx), (uint32_t)(p.th * d.sy), (uint32_t)p.tn};
+    uint32_t estr[4] = {1, (uint32_t)d.sx, (uint32_t)d.sy, 1};
+    // degenerate outer dims must still carry a legal (multiple of 16 B) stride
+    for (int i = 0; i < 3; ++i)
+      if (strides[i] == 0) strides[i] = (i == 0 ? (uint64_t)d.Cin * 2 : strides[i - 1]);
+    int r;
+    if (d.im2col) {
+      // Bounding box [lower, dim-1+upper] holds exactly the W_out x H_out base pixels (spaced by
+      // the traversal stride); the per-tap offsets (kx*dil, ky*dil) are given at load time.
+      int lower[2] = {-d.pad_x, -d.pad_y};
+      int upper[2] = {(d.W_out - 1) * d.sx - d.pad_x - (d.W - 1),
+                      (d.H_out - 1) * d.sy - d.pad_y - (d.H - 1)};
+      r = encode_im2col_bf16(&plan->tmA, d.x, dims, strides, lower, upper, 64, 128, estr, 1);
+    } else {
+      r = encode_tiled_bf16(&plan->tmA, d.x, 4, dims, strides, box, estr);
+    }
+    if (r) return r;
+  }
+  {
+    const uint64_t K = (uint64_t)d.kh * d.kw * d.cin_pad;
+    uint64_t dims[2] = {K, (uint64_t)d.cout_pad};
+    uint64_t strides[1] = {K * 2};
+    uint32_t box[2] = {64, (uint32_t)block_n};
+    uint32_t estr[2] = {1, 1};
+    int r = encode_tiled_bf16(&plan->tmB, d.w, 2, dims, strides, box, estr);
+    if (r) return r;
+  }
+  const long long total_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
+  plan->grid = (int)(total_tiles < num_sms ? total_tiles : num_sms);
+  if (plan->grid < 1) plan->grid = 1;
+  plan->flops = 2.0 * d.N * d.H_out * d.W_out * (double)d.cout_pad * d.kh * d.kw * d.Cin;
+  return 0;
+}
+
+int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
+  static int smem_set = 0;
+  if (smem_set < plan.smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("conv: smem attr: %s", cudaGetErrorString(e)); return -3; }
+    smem_set = 227 * 1024;
+  }
+  conv_igemm_kernel<<<plan.grid, kThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("conv launch: %s", cudaGetErrorString(e)); return -4; }
+  return 0;
+}
+
+}  // namespace dpb
