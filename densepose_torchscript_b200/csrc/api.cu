@@ -1,6 +1,10 @@
 // C-ABI entry points (include/dpb200.h). Only plain C types cross this boundary.
+// (model / session entry points live in engine.cu)
 #include "../../include/dpb200.h"
 #include "conv_igemm.cuh"
+#include "kernels.cuh"
+
+#include <string.h>
 
 namespace {
 int num_sms() {
@@ -11,7 +15,10 @@ int num_sms() {
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
   return sms;
 }
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 }  // namespace
+
+using namespace dpb;
 
 extern "C" {
 
@@ -46,7 +53,95 @@ int dpb200_conv2d(const dpb200_conv2d_args* a, void* stream) {
   dpb::ConvPlan plan;
   int r = dpb::conv_plan_build(&plan, d, num_sms());
   if (r) return r;
-  return dpb::conv_plan_launch(plan, static_cast<cudaStream_t>(stream));
+  return dpb::conv_plan_launch(plan, S(stream));
+}
+
+int dpb200_preprocess(const dpb200_preprocess_args* a, void* stream) {
+  if (!a) { set_error("preprocess: null args"); return -1; }
+  PreprocessArgs p{};
+  p.src = a->src; p.src_u8 = a->src_u8; p.B = a->b; p.H0 = a->h0; p.W0 = a->w0; p.Hr = a->hr; p.Wr = a->wr;
+  p.inv_scale = a->inv_scale; p.flip_rgb = a->flip_rgb;
+  for (int i = 0; i < 3; ++i) { p.mean[i] = a->mean[i]; p.std[i] = a->std[i]; }
+  p.dst = reinterpret_cast<bf16*>(a->dst); p.Hp = a->hp; p.Wx = a->wx;
+  return launch_preprocess(p, S(stream));
+}
+
+int dpb200_maxpool3x3s2(const void* x, void* y, int32_t b, int32_t h, int32_t w, int32_t c, void* stream) {
+  return launch_maxpool3x3s2((const bf16*)x, (bf16*)y, b, h, w, c, S(stream));
+}
+int dpb200_upsample2x(const void* x, void* y, int32_t b, int32_t h, int32_t w, int32_t c, void* stream) {
+  return launch_upsample2x((const bf16*)x, (bf16*)y, b, h, w, c, S(stream));
+}
+int dpb200_decoder_merge(const void* a, const void* b3, const void* b4, const void* b5, void* out, int32_t b,
+                         int32_t h, int32_t w, int32_t c, void* stream) {
+  return launch_decoder_merge((const bf16*)a, (const bf16*)b3, (const bf16*)b4, (const bf16*)b5, (bf16*)out, b, h,
+                              w, c, S(stream));
+}
+
+int dpb200_rpn_proposals(const dpb200_rpn_args* a, void* stream) {
+  if (!a) { set_error("rpn: null args"); return -1; }
+  RpnArgs r{};
+  for (int l = 0; l < 5; ++l) {
+    r.lvl[l].head = a->head[l]; r.lvl[l].H = a->h[l]; r.lvl[l].W = a->w[l]; r.lvl[l].stride = a->stride[l];
+    memcpy(r.lvl[l].anchors, a->anchors[l], sizeof(float) * 12);
+  }
+  r.B = a->b; r.pre_topk = a->pre_topk; r.post_topk = a->post_topk; r.nms_thresh = a->nms_thresh;
+  r.clip_x = a->clip_x; r.clip_y = a->clip_y;
+  r.cand_boxes = a->cand_boxes; r.cand_scores = a->cand_scores; r.cand_count = a->cand_count;
+  r.cand_keep = a->cand_keep; r.prop_boxes = a->prop_boxes; r.prop_scores = a->prop_scores;
+  r.prop_count = a->prop_count;
+  int rc = launch_rpn_topk_decode(r, S(stream));
+  if (rc) return rc;
+  rc = launch_rpn_nms(r, S(stream));
+  if (rc) return rc;
+  return launch_rpn_merge(r, S(stream));
+}
+
+int dpb200_nms_sorted(const float* boxes, int32_t n, float thr, uint8_t* keep, void* stream) {
+  return launch_nms_sorted(boxes, n, thr, keep, S(stream));
+}
+
+int dpb200_roi_align(const dpb200_roi_align_args* a, void* stream) {
+  if (!a) { set_error("roi_align: null args"); return -1; }
+  RoiAlignArgs r{};
+  for (int l = 0; l < 4; ++l) { r.feat[l] = (const bf16*)a->feat[l]; r.H[l] = a->h[l]; r.W[l] = a->w[l]; r.scale[l] = a->scale[l]; }
+  r.n_levels = a->n_levels; r.C = a->c; r.rois = a->rois; r.n_rois = a->n_rois; r.R = a->r; r.P = a->p;
+  r.out = a->out; r.out_fp32 = a->out_fp32;
+  return launch_roi_align(r, S(stream));
+}
+
+int dpb200_box_predict(const dpb200_box_predict_args* a, void* stream) {
+  if (!a) { set_error("box_predict: null args"); return -1; }
+  BoxPredictArgs p{};
+  p.head = a->head; p.prop_boxes = a->prop_boxes; p.prop_count = a->prop_count; p.B = a->b; p.R = a->r;
+  p.score_thresh = a->score_thresh; p.nms_thresh = a->nms_thresh; p.topk = a->topk;
+  p.scale_x = a->scale_x; p.scale_y = a->scale_y; p.out_w = a->out_w; p.out_h = a->out_h;
+  p.ws_boxes = a->ws_boxes; p.ws_keep = a->ws_keep;
+  p.det_boxes_raw = a->det_boxes_raw; p.det_boxes = a->det_boxes; p.det_scores = a->det_scores;
+  p.det_count = a->det_count;
+  return launch_box_predict(p, S(stream));
+}
+
+int dpb200_groupnorm_relu(const void* x, const float* gamma, const float* beta, void* y, int32_t r, int32_t hw,
+                          int32_t c, int32_t y_cstride, int32_t out_hw, const int32_t* n_valid, void* stream) {
+  return launch_groupnorm_relu((const bf16*)x, gamma, beta, (bf16*)y, r, hw, c, y_cstride, out_hw, n_valid, S(stream));
+}
+int dpb200_avgpool(const void* x, void* y, int32_t r, int32_t hw, int32_t c, const int32_t* n_valid, void* stream) {
+  return launch_avgpool((const bf16*)x, (bf16*)y, r, hw, c, n_valid, S(stream));
+}
+int dpb200_predictor_upsample(const float* low, int32_t r, int32_t s, int32_t cpad, int32_t kc,
+                              const int32_t* n_valid, float* coarse, float* fine, float* u, float* v,
+                              void* stream) {
+  return launch_predictor_upsample(low, r, s, cpad, kc, n_valid, coarse, fine, u, v, S(stream));
+}
+
+int dpb200_dp_resample(const dpb200_resample_args* a, void* stream) {
+  if (!a) { set_error("dp_resample: null args"); return -1; }
+  ResampleArgs r{};
+  r.coarse = a->coarse; r.fine = a->fine; r.u = a->u; r.v = a->v; r.D = a->d; r.Kc = a->kc; r.S = a->s;
+  r.box_wh = a->box_wh; r.offsets = (const long long*)a->offsets; r.labels = (long long*)a->labels;
+  r.uv = a->uv; r.total_pixels = a->total_pixels;
+  return launch_dp_resample(r, S(stream));
 }
 
 }  // extern "C"

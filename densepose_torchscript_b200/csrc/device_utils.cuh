@@ -1,0 +1,120 @@
+// Block-level device helpers shared by rpn.cu and roi.cu: order-preserving float keys, bitonic sort,
+// block scan, and the greedy NMS on score-sorted boxes (torchvision nms semantics).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dpb {
+
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// Descending bitonic sort of N (power of two) 64-bit keys in shared memory by the whole block.
+static __device__ void bitonic_sort_desc(unsigned long long* keys, int N) {
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], b = keys[ixj];
+          const bool desc = ((i & k) == 0);
+          if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Block-wide inclusive scan of one unsigned per thread (blockDim.x == 1024).
+__device__ __forceinline__ unsigned block_scan_incl(unsigned v, unsigned* warp_sums) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) warp_sums[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  if (warp > 0) v += warp_sums[warp - 1];
+  __syncthreads();
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------- NMS
+// boxes sorted by descending score; alive[] marks usable entries on entry; keep[] on exit.
+// Shared: mask [n][32] u32 (bit j of row i: j > i and IoU(i, j) > thr), boxes [n] float4, areas [n].
+static __device__ void nms_sorted_block(const float4* __restrict__ g_boxes, int n, float thr,
+                                 unsigned char* __restrict__ keep_io, uint32_t* smem) {
+  uint32_t* mask = smem;                                  // n * 32
+  float4* boxes = reinterpret_cast<float4*>(smem + 1024 * 32);
+  float* areas = reinterpret_cast<float*>(boxes + 1024);
+  uint32_t* alive_words = reinterpret_cast<uint32_t*>(areas + 1024);   // 32
+  if (threadIdx.x < 32) alive_words[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float4 bx = g_boxes[i];
+    boxes[i] = bx;
+    areas[i] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+    if (keep_io[i]) atomicOr(&alive_words[i >> 5], 1u << (i & 31));
+  }
+  __syncthreads();
+  const int nw = (n + 31) >> 5;
+  for (int item = threadIdx.x; item < n * nw; item += blockDim.x) {
+    const int i = item / nw, w = item - i * nw;
+    uint32_t bits = 0;
+    const int j0 = w * 32;
+    if (j0 + 31 > i) {
+      const float4 bi = boxes[i];
+      const float ai = areas[i];
+      const int jend = (j0 + 32 < n) ? j0 + 32 : n;
+      for (int j = (j0 > i + 1 ? j0 : i + 1); j < jend; ++j) {
+        const float4 bj = boxes[j];
+        const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+        const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+        const float w_ = fmaxf(0.f, __fsub_rn(xx2, xx1)), h_ = fmaxf(0.f, __fsub_rn(yy2, yy1));
+        const float inter = __fmul_rn(w_, h_);
+        const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, areas[j]), inter));
+        if (ovr > thr) bits |= 1u << (j - j0);
+      }
+    }
+    mask[i * 32 + w] = bits;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    uint32_t removed = ~alive_words[lane];
+    uint32_t kept = 0;
+    for (int i = 0; i < n; ++i) {
+      const uint32_t r = __shfl_sync(0xffffffffu, removed, i >> 5);
+      if (!((r >> (i & 31)) & 1u)) {
+        if (lane == (i >> 5)) kept |= 1u << (i & 31);
+        if (lane < nw) removed |= mask[i * 32 + lane];
+      }
+    }
+    alive_words[lane] = kept;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    keep_io[i] = (alive_words[i >> 5] >> (i & 31)) & 1u;
+}
+
+
+static constexpr int kNmsSmemBytes = 1024 * 32 * 4 + 1024 * 16 + 1024 * 4 + 32 * 4;
+
+}  // namespace dpb

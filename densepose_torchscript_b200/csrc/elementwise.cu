@@ -1,0 +1,397 @@
+// HBM-bound elementwise / resampling kernels: preprocess, maxpool, bilinear x2, decoder merge,
+// GroupNorm+ReLU, average pool, predictor tail. All NHWC, 16-byte vector accesses, grid-stride.
+#include "kernels.cuh"
+#include "conv_igemm.cuh"
+#include "ptx.cuh"
+
+namespace dpb {
+
+static inline int grid_for(long long work, int threads, int cap = 148 * 16) {
+  long long g = (work + threads - 1) / threads;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+#define DPB_CHECK_LAUNCH(name)                                                     \
+  do {                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                          \
+    if (e__ != cudaSuccess) {                                                      \
+      set_error("%s launch: %s", name, cudaGetErrorString(e__));                   \
+      return -4;                                                                   \
+    }                                                                              \
+  } while (0)
+
+// ------------------------------------------------------------------------------------ preprocess
+// ATen upsample_bilinear2d (align_corners=False, scale_factor given): src = s*(dst+0.5)-0.5, s = 1/k.
+__device__ __forceinline__ void src_index(float scale, int dst, int in_size, int& i0, int& i1,
+                                          float& l0, float& l1) {
+  float real = __fsub_rn(__fmul_rn(scale, (float)dst + 0.5f), 0.5f);
+  if (real < 0.f) real = 0.f;
+  i0 = (int)real;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = fminf(fmaxf(__fsub_rn(real, (float)i0), 0.f), 1.f);
+  l0 = __fsub_rn(1.f, l1);
+}
+
+template <typename T>
+__global__ void preprocess_kernel(PreprocessArgs a) {
+  const long long total = (long long)a.B * a.Hp * a.Wx;
+  const T* src = reinterpret_cast<const T*>(a.src);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int xc = (int)(i % a.Wx);
+    const int y = (int)((i / a.Wx) % a.Hp);
+    const int b = (int)(i / ((long long)a.Wx * a.Hp));
+    const int x = xc - 3;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (x >= 0 && x < a.Wr && y < a.Hr) {
+      int y0, y1, x0, x1;
+      float ly0, ly1, lx0, lx1;
+      src_index(a.inv_scale, y, a.H0, y0, y1, ly0, ly1);
+      src_index(a.inv_scale, x, a.W0, x0, x1, lx0, lx1);
+      const T* base = src + (long long)b * a.H0 * a.W0 * 3;
+      const T* p00 = base + ((long long)y0 * a.W0 + x0) * 3;
+      const T* p01 = base + ((long long)y0 * a.W0 + x1) * 3;
+      const T* p10 = base + ((long long)y1 * a.W0 + x0) * 3;
+      const T* p11 = base + ((long long)y1 * a.W0 + x1) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int cs = a.flip_rgb ? 2 - c : c;
+        const float top = __fadd_rn(__fmul_rn(lx0, (float)p00[cs]), __fmul_rn(lx1, (float)p01[cs]));
+        const float bot = __fadd_rn(__fmul_rn(lx0, (float)p10[cs]), __fmul_rn(lx1, (float)p11[cs]));
+        float r = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+        if (sizeof(T) == 1) r = fminf(fmaxf(rintf(r), 0.f), 255.f);  // uint8 images stay uint8 in the reference
+        v[c] = __fdiv_rn(__fsub_rn(r, a.mean[c]), a.std[c]);
+      }
+    }
+    uint2 o;
+    o.x = pack_bf16(v[0], v[1]);
+    o.y = pack_bf16(v[2], 0.f);
+    reinterpret_cast<uint2*>(a.dst)[i] = o;
+  }
+}
+
+int launch_preprocess(const PreprocessArgs& a, cudaStream_t s) {
+  const long long total = (long long)a.B * a.Hp * a.Wx;
+  const int g = grid_for(total, 256);
+  if (a.src_u8) preprocess_kernel<unsigned char><<<g, 256, 0, s>>>(a);
+  else preprocess_kernel<float><<<g, 256, 0, s>>>(a);
+  DPB_CHECK_LAUNCH("preprocess");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ max pool
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+__global__ void maxpool3x3s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H,
+                                    int W, int C8, int Ho, int Wo) {
+  const long long total = (long long)B * Ho * Wo * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    const int ox = (int)((i / C8) % Wo);
+    const int oy = (int)((i / ((long long)C8 * Wo)) % Ho);
+    const int b = (int)(i / ((long long)C8 * Wo * Ho));
+    uint4 m;
+    bool first = true;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int iy = oy * 2 + dy;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int ix = ox * 2 + dx;
+        if (ix < 0 || ix >= W) continue;
+        const uint4 v = __ldg(x + (((long long)b * H + iy) * W + ix) * C8 + c);
+        if (first) { m = v; first = false; }
+        else { m.x = bf16x2_max(m.x, v.x); m.y = bf16x2_max(m.y, v.y); m.z = bf16x2_max(m.z, v.z); m.w = bf16x2_max(m.w, v.w); }
+      }
+    }
+    y[i] = m;
+  }
+}
+
+int launch_maxpool3x3s2(const bf16* x, bf16* y, int B, int H, int W, int C, cudaStream_t s) {
+  if (C % 8) { set_error("maxpool: C %% 8 != 0"); return -1; }
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)B * Ho * Wo * (C / 8);
+  maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x),
+                                                          reinterpret_cast<uint4*>(y), B, H, W, C / 8, Ho, Wo);
+  DPB_CHECK_LAUNCH("maxpool");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ bilinear x2
+__device__ __forceinline__ void up2_index(int dst, int in_size, int& i0, int& i1, float& l1) {
+  float real = 0.5f * ((float)dst + 0.5f) - 0.5f;   // exact in fp32
+  if (real < 0.f) real = 0.f;
+  i0 = (int)real;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = real - (float)i0;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+  o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  return o;
+}
+
+// acc += bilinear sample of the half-resolution tensor `x` ([.., h, w, C8]) at output pixel (oy, ox)
+__device__ __forceinline__ void add_up2(const uint4* __restrict__ x, int b, int h, int w, int C8, int c,
+                                        int oy, int ox, float* acc) {
+  int y0, y1, x0, x1;
+  float ly, lx;
+  up2_index(oy, h, y0, y1, ly);
+  up2_index(ox, w, x0, x1, lx);
+  const uint4* base = x + (long long)b * h * w * C8 + c;
+  float v00[8], v01[8], v10[8], v11[8];
+  unpack8(__ldg(base + ((long long)y0 * w + x0) * C8), v00);
+  unpack8(__ldg(base + ((long long)y0 * w + x1) * C8), v01);
+  unpack8(__ldg(base + ((long long)y1 * w + x0) * C8), v10);
+  unpack8(__ldg(base + ((long long)y1 * w + x1) * C8), v11);
+  const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    acc[i] += hy * (hx * v00[i] + lx * v01[i]) + ly * (hx * v10[i] + lx * v11[i]);
+}
+
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W,
+                                  int C8) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)B * Ho * Wo * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    const int ox = (int)((i / C8) % Wo);
+    const int oy = (int)((i / ((long long)C8 * Wo)) % Ho);
+    const int b = (int)(i / ((long long)C8 * Wo * Ho));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    add_up2(x, b, H, W, C8, c, oy, ox, acc);
+    y[i] = pack8(acc);
+  }
+}
+
+int launch_upsample2x(const bf16* x, bf16* y, int B, int H, int W, int C, cudaStream_t s) {
+  if (C % 8) { set_error("upsample2x: C %% 8 != 0"); return -1; }
+  const long long total = (long long)B * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x),
+                                                        reinterpret_cast<uint4*>(y), B, H, W, C / 8);
+  DPB_CHECK_LAUNCH("upsample2x");
+  return 0;
+}
+
+__global__ void decoder_merge_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b3,
+                                     const uint4* __restrict__ b4, const uint4* __restrict__ b5,
+                                     uint4* __restrict__ out, int B, int H, int W, int C8) {
+  const long long total = (long long)B * H * W * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    const int ox = (int)((i / C8) % W);
+    const int oy = (int)((i / ((long long)C8 * W)) % H);
+    const int b = (int)(i / ((long long)C8 * W * H));
+    float acc[8];
+    unpack8(__ldg(a + i), acc);
+    // reference order: ((p2 + up(p3)) + up(p4)) + up(p5)   (roi_head.py:73-77)
+    add_up2(b3, b, H / 2, W / 2, C8, c, oy, ox, acc);
+    add_up2(b4, b, H / 2, W / 2, C8, c, oy, ox, acc);
+    add_up2(b5, b, H / 2, W / 2, C8, c, oy, ox, acc);
+    out[i] = pack8(acc);
+  }
+}
+
+int launch_decoder_merge(const bf16* a, const bf16* b, const bf16* c, const bf16* d, bf16* out, int B,
+                         int H, int W, int C, cudaStream_t s) {
+  if (C % 8 || H % 2 || W % 2) { set_error("decoder_merge: bad shape"); return -1; }
+  const long long total = (long long)B * H * W * (C / 8);
+  decoder_merge_kernel<<<grid_for(total, 256), 256, 0, s>>>(
+      reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
+      reinterpret_cast<const uint4*>(c), reinterpret_cast<const uint4*>(d),
+      reinterpret_cast<uint4*>(out), B, H, W, C / 8);
+  DPB_CHECK_LAUNCH("decoder_merge");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ GroupNorm + ReLU
+// One CTA per ROI. 32 groups; a 16-byte chunk (8 channels) never straddles a group (C/32 is 8 or 16).
+__global__ void __launch_bounds__(512)
+groupnorm_relu_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, bf16* __restrict__ y, int HW, int C,
+                      int y_cstride, int out_hw, const int* __restrict__ n_valid) {
+  const int r = blockIdx.x;
+  if (n_valid != nullptr && r >= *n_valid) return;
+  __shared__ double s_sum[32], s_sq[32];
+  __shared__ float s_mean[32], s_rstd[32];
+  if (threadIdx.x < 32) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
+  __syncthreads();
+  const int C8 = C / 8;
+  const int cpg = C / 32;
+  const uint4* xr = x + (long long)r * HW * C8;
+  // each thread owns one channel chunk; pixels strided
+  const int chunk = threadIdx.x % C8;
+  const int pstart = threadIdx.x / C8;
+  const int pstep = blockDim.x / C8;
+  float sum = 0.f, sq = 0.f;
+  for (int p = pstart; p < HW; p += pstep) {
+    float f[8];
+    unpack8(__ldg(xr + (long long)p * C8 + chunk), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sum += f[i]; sq += f[i] * f[i]; }
+  }
+  const int grp = (chunk * 8) / cpg;
+  atomicAdd(&s_sum[grp], (double)sum);
+  atomicAdd(&s_sq[grp], (double)sq);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const double n = (double)HW * cpg;
+    const double m = s_sum[threadIdx.x] / n;
+    double var = s_sq[threadIdx.x] / n - m * m;
+    if (var < 0) var = 0;
+    s_mean[threadIdx.x] = (float)m;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  float g[8], bt[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { g[i] = gamma[chunk * 8 + i]; bt[i] = beta[chunk * 8 + i]; }
+  const float mean = s_mean[grp], rstd = s_rstd[grp];
+  if (out_hw == HW) {
+    for (int p = pstart; p < HW; p += pstep) {
+      float f[8];
+      unpack8(__ldg(xr + (long long)p * C8 + chunk), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaxf((f[i] - mean) * rstd * g[i] + bt[i], 0.f);
+      *reinterpret_cast<uint4*>(y + ((long long)r * out_hw + p) * y_cstride + chunk * 8) = pack8(f);
+    }
+  } else {
+    // HW == 1: normalise the single pixel and broadcast it (bilinear from 1x1 is a broadcast)
+    float f[8];
+    unpack8(__ldg(xr + chunk), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaxf((f[i] - mean) * rstd * g[i] + bt[i], 0.f);
+    const uint4 o = pack8(f);
+    for (int p = pstart; p < out_hw; p += pstep)
+      *reinterpret_cast<uint4*>(y + ((long long)r * out_hw + p) * y_cstride + chunk * 8) = o;
+  }
+}
+
+int launch_groupnorm_relu(const bf16* x, const float* gamma, const float* beta, bf16* y, int R, int HW,
+                          int C, int y_cstride, int out_hw, const int* n_valid, cudaStream_t s) {
+  if (C % 256 != 0 || C > 512 * 8 || (out_hw != HW && HW != 1)) { set_error("groupnorm: bad shape"); return -1; }
+  const int C8 = C / 8;
+  int threads = 512;
+  if (threads % C8) { set_error("groupnorm: C/8 must divide 512"); return -1; }
+  groupnorm_relu_kernel<<<R, threads, 0, s>>>(reinterpret_cast<const uint4*>(x), gamma, beta, y, HW, C,
+                                              y_cstride, out_hw, n_valid);
+  DPB_CHECK_LAUNCH("groupnorm_relu");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ average pool
+__global__ void avgpool_kernel(const uint4* __restrict__ x, bf16* __restrict__ y, int HW, int C8,
+                               const int* __restrict__ n_valid) {
+  const int r = blockIdx.x;
+  if (n_valid != nullptr && r >= *n_valid) return;
+  extern __shared__ float s_acc[];   // [C8*8]
+  for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int chunk = threadIdx.x % C8;
+  const int pstart = threadIdx.x / C8, pstep = blockDim.x / C8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = pstart; p < HW; p += pstep) {
+    float f[8];
+    unpack8(__ldg(x + ((long long)r * HW + p) * C8 + chunk), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += f[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(&s_acc[chunk * 8 + i], acc[i]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x)
+    y[(long long)r * C8 * 8 + i] = __float2bfloat16(s_acc[i] / (float)HW);
+}
+
+int launch_avgpool(const bf16* x, bf16* y, int R, int HW, int C, const int* n_valid, cudaStream_t s) {
+  if (C % 8 || 256 % (C / 8)) { set_error("avgpool: bad C"); return -1; }
+  avgpool_kernel<<<R, 256, C * sizeof(float), s>>>(reinterpret_cast<const uint4*>(x), y, HW, C / 8, n_valid);
+  DPB_CHECK_LAUNCH("avgpool");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ predictor tail
+// CTA (k, roi): stages low-res rows (k, k+1) in shared memory and writes output rows 2k+1, 2k+2 of every
+// channel plane with x-contiguous (coalesced) NCHW stores. k in [-1, S-1].
+__global__ void __launch_bounds__(256)
+predictor_upsample_kernel(const float* __restrict__ low, int S, int Cpad, int Kc,
+                          const int* __restrict__ n_valid, float* __restrict__ coarse,
+                          float* __restrict__ fine, float* __restrict__ u, float* __restrict__ v) {
+  const int r = blockIdx.y;
+  if (n_valid != nullptr && r >= *n_valid) return;
+  const int k = (int)blockIdx.x - 1;
+  const int r0 = k < 0 ? 0 : k, r1 = (k + 1 > S - 1) ? S - 1 : k + 1;
+  extern __shared__ float sm[];            // [2][S][Cs]
+  const int Cs = Cpad + 1;                 // padded channel stride: conflict-free column reads
+  const float* src0 = low + ((long long)r * S + r0) * S * Cpad;
+  const float* src1 = low + ((long long)r * S + r1) * S * Cpad;
+  for (int i = threadIdx.x; i < S * Cpad; i += blockDim.x) {
+    const int xx = i / Cpad, c = i - xx * Cpad;
+    sm[xx * Cs + c] = __ldg(src0 + i);
+    sm[(S + xx) * Cs + c] = __ldg(src1 + i);
+  }
+  __syncthreads();
+  const int So = 2 * S;
+  const int C = Kc + 75;
+  for (int half = 0; half < 2; ++half) {
+    const int oy = 2 * k + 1 + half;
+    if (oy < 0 || oy >= So) continue;
+    // oy = 2k+1: rows (k, k+1) weights (0.75, 0.25); oy = 2k+2: weights (0.25, 0.75); edges collapse.
+    int y0, y1; float ly;
+    up2_index(oy, S, y0, y1, ly);
+    const int s0 = (y0 == r0) ? 0 : 1, s1 = (y1 == r0) ? 0 : 1;
+    const float hy = 1.f - ly;
+    for (int i = threadIdx.x; i < C * So; i += blockDim.x) {
+      const int c = i / So, ox = i - c * So;
+      int x0, x1; float lx;
+      up2_index(ox, S, x0, x1, lx);
+      const float hx = 1.f - lx;
+      const float v00 = sm[(s0 * S + x0) * Cs + c], v01 = sm[(s0 * S + x1) * Cs + c];
+      const float v10 = sm[(s1 * S + x0) * Cs + c], v11 = sm[(s1 * S + x1) * Cs + c];
+      const float val = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+      float* dst; int cc, nc;
+      if (c < Kc) { dst = coarse; cc = c; nc = Kc; }
+      else if (c < Kc + 25) { dst = fine; cc = c - Kc; nc = 25; }
+      else if (c < Kc + 50) { dst = u; cc = c - Kc - 25; nc = 25; }
+      else { dst = v; cc = c - Kc - 50; nc = 25; }
+      dst[(((long long)r * nc + cc) * So + oy) * So + ox] = val;
+    }
+  }
+}
+
+int launch_predictor_upsample(const float* low, int R, int S, int Cpad, int Kc, const int* n_valid,
+                              float* coarse, float* fine, float* u, float* v, cudaStream_t s) {
+  const size_t smem = (size_t)2 * S * (Cpad + 1) * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem_set < smem) {
+    cudaError_t e = cudaFuncSetAttribute(predictor_upsample_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("predictor_upsample smem: %s", cudaGetErrorString(e)); return -3; }
+    smem_set = smem;
+  }
+  if (R == 0) return 0;
+  dim3 grid(S + 1, R);
+  predictor_upsample_kernel<<<grid, 256, smem, s>>>(low, S, Cpad, Kc, n_valid, coarse, fine, u, v);
+  DPB_CHECK_LAUNCH("predictor_upsample");
+  return 0;
+}
+
+}  // namespace dpb

@@ -1,0 +1,539 @@
+// Whole-graph forward: model (named packed weights) + session (launch plan over a caller workspace).
+// The plan is a flat list of ops built once per (batch, image size); run() replays it on one stream
+// with no host synchronisation — all dynamic counts (proposals, detections) stay on the device.
+//
+// Reference call stack reproduced: DefaultPredictor.forward (engine/defaults.py:65-97) ->
+// GeneralizedRCNN.inference (meta_arch/rcnn.py:110-154): preprocess -> ResNet+FPN -> RPN ->
+// StandardROIHeads._forward_box -> DensePoseROIHeads._forward_densepose -> detector_postprocess.
+#include "../../include/dpb200.h"
+#include "conv_igemm.cuh"
+#include "kernels.cuh"
+
+#include <math.h>
+#include <string.h>
+
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace dpb;
+
+struct Weight { const void* d0; const void* d1; int cin_pad, cout_pad; };
+
+struct dpb200_model {
+  dpb200_model_config cfg;
+  std::map<std::string, Weight> w;
+  int num_sms = 148;
+};
+
+struct TensorInfo { void* p; int64_t shape[4]; int dtype; };
+
+struct T4 {           // NHWC activation
+  void* p = nullptr; int N = 0, H = 0, W = 0, C = 0; int fp32 = 0;
+  long long elems() const { return (long long)N * H * W * C; }
+};
+
+struct dpb200_session {
+  const dpb200_model* m = nullptr;
+  int B = 0, H0 = 0, W0 = 0, src_u8 = 0;
+  int Hr = 0, Wr = 0, Hp = 0, Wp = 0, Wx = 0;
+  double k = 1.0;
+  char* ws = nullptr; size_t ws_bytes = 0, ws_used = 0;
+  bool dry = false;     // dry run: only measure the workspace
+  std::vector<std::function<int(cudaStream_t)>> ops;
+  std::vector<ConvPlan*> plans;
+  std::map<std::string, TensorInfo> taps;
+  double flops = 0;
+  // run-time bound pointers
+  const dpb200_forward_io* io = nullptr;
+  // fixed workspace objects needed by run()
+  PreprocessArgs pre{};
+  BoxPredictArgs bp{};
+  float* rois_dp = nullptr; int* dp_total = nullptr; int* dp_offsets = nullptr;
+  float* low = nullptr; int low_S = 0, low_C = 0;
+  std::string err;
+  ~dpb200_session() { for (auto* p : plans) delete p; }
+};
+
+namespace {
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct Builder {
+  dpb200_session* s;
+  const dpb200_model* m;
+  int fail = 0;
+
+  void* alloc(size_t bytes) {
+    size_t off = (s->ws_used + 1023) & ~(size_t)1023;
+    s->ws_used = off + bytes;
+    if (s->dry) return reinterpret_cast<void*>(0x10000 + off);   // fake, never dereferenced
+    if (s->ws_used > s->ws_bytes) { fail = -10; set_error("session: workspace too small"); return nullptr; }
+    return s->ws + off;
+  }
+  T4 act(int N, int H, int W, int C, int fp32 = 0) {
+    T4 t; t.N = N; t.H = H; t.W = W; t.C = C; t.fp32 = fp32;
+    t.p = alloc((size_t)t.elems() * (fp32 ? 4 : 2));
+    return t;
+  }
+  void tap(const std::string& name, const T4& t) {
+    TensorInfo ti; ti.p = t.p; ti.shape[0] = t.N; ti.shape[1] = t.H; ti.shape[2] = t.W; ti.shape[3] = t.C;
+    ti.dtype = t.fp32 ? 1 : 0;
+    s->taps[name] = ti;
+  }
+  void tap_raw(const std::string& name, void* p, int64_t a, int64_t b, int64_t c, int64_t d, int dtype) {
+    TensorInfo ti; ti.p = p; ti.shape[0] = a; ti.shape[1] = b; ti.shape[2] = c; ti.shape[3] = d; ti.dtype = dtype;
+    s->taps[name] = ti;
+  }
+  const Weight* weight(const std::string& name) {
+    auto it = m->w.find(name);
+    if (it == m->w.end()) { fail = -11; set_error("model: missing weight '%s'", name.c_str()); return nullptr; }
+    return &it->second;
+  }
+
+  struct ConvOpt {
+    int k = 1, stride = 1, pad = 0, dil = 1, relu = 0;
+    const T4* res = nullptr; int res_shift = 0;
+    const int* n_valid = nullptr;
+    int kh = 0, kw = 0, pad_y = -1, pad_x = -1, sy = 0, sx = 0;       // overrides
+    long long x_sw = 0, x_sh = 0, x_sn = 0;                           // input stride overrides (elements)
+    long long out_sn = 0, out_sy = 0, out_sx = 0; long long out_off = 0;   // output view overrides
+    int H_out = 0, W_out = 0;
+    bool no_bias = false;
+  };
+
+  // y must be allocated by the caller (so views / slices are possible)
+  void conv(const std::string& wname, const T4& x, const T4& y, const ConvOpt& o) {
+    if (fail) return;
+    const Weight* w = weight(wname);
+    if (!w) return;
+    ConvDesc d;
+    d.x = x.p; d.N = x.N; d.H = x.H; d.W = x.W; d.Cin = x.C;
+    d.x_sw = o.x_sw ? o.x_sw : x.C;
+    d.x_sh = o.x_sh ? o.x_sh : d.x_sw * x.W;
+    d.x_sn = o.x_sn ? o.x_sn : d.x_sh * x.H;
+    d.w = w->d0; d.cin_pad = w->cin_pad; d.cout_pad = w->cout_pad;
+    d.bias = o.no_bias ? nullptr : reinterpret_cast<const float*>(w->d1);
+    d.kh = o.kh ? o.kh : o.k; d.kw = o.kw ? o.kw : o.k;
+    d.sy = o.sy ? o.sy : o.stride; d.sx = o.sx ? o.sx : o.stride;
+    d.pad_y = o.pad_y >= 0 ? o.pad_y : o.pad; d.pad_x = o.pad_x >= 0 ? o.pad_x : o.pad;
+    d.dil = o.dil;
+    d.H_out = o.H_out ? o.H_out : (x.H + 2 * d.pad_y - d.dil * (d.kh - 1) - 1) / d.sy + 1;
+    d.W_out = o.W_out ? o.W_out : (x.W + 2 * d.pad_x - d.dil * (d.kw - 1) - 1) / d.sx + 1;
+    d.relu = o.relu;
+    if (o.res) {
+      d.res = o.res->p; d.res_sx = o.res->C; d.res_sy = (long long)o.res->C * o.res->W;
+      d.res_sn = d.res_sy * o.res->H; d.res_shift = o.res_shift;
+    }
+    d.out_fp32 = y.fp32;
+    d.out_sx = o.out_sx ? o.out_sx : y.C;
+    d.out_sy = o.out_sy ? o.out_sy : d.out_sx * y.W;
+    d.out_sn = o.out_sn ? o.out_sn : d.out_sy * y.H;
+    d.out = y.fp32 ? (void*)(reinterpret_cast<float*>(y.p) + o.out_off)
+                   : (void*)(reinterpret_cast<bf16*>(y.p) + o.out_off);
+    d.n_valid = o.n_valid;
+    if (d.cout_pad > y.C && !o.out_sx) { fail = -12; set_error("conv %s: output has %d channels, weights %d", wname.c_str(), y.C, d.cout_pad); return; }
+    s->flops += 2.0 * x.N * d.H_out * d.W_out * (double)w->cout_pad * d.kh * d.kw * w->cin_pad;
+    if (s->dry) { s->ops.push_back([](cudaStream_t) { return 0; }); return; }
+    ConvPlan* plan = new ConvPlan();
+    int r = conv_plan_build(plan, d, m->num_sms);
+    if (r) { fail = r; delete plan; return; }
+    s->plans.push_back(plan);
+    s->ops.push_back([plan](cudaStream_t st) { return conv_plan_launch(*plan, st); });
+  }
+  void op(std::function<int(cudaStream_t)> f) {
+    if (fail) return;
+    if (s->dry) { s->ops.push_back([](cudaStream_t) { return 0; }); return; }
+    s->ops.push_back(std::move(f));
+  }
+};
+
+void cell_anchors(float size, float* out12) {
+  // anchor_generator.py:203-216 (python float = double, then torch.tensor -> fp32)
+  const double ratios[3] = {0.5, 1.0, 2.0};
+  const double area = (double)size * size;
+  for (int i = 0; i < 3; ++i) {
+    const double w = sqrt(area / ratios[i]);
+    const double h = ratios[i] * w;
+    out12[i * 4 + 0] = (float)(-w / 2.0); out12[i * 4 + 1] = (float)(-h / 2.0);
+    out12[i * 4 + 2] = (float)(w / 2.0);  out12[i * 4 + 3] = (float)(h / 2.0);
+  }
+}
+
+int build_plan(dpb200_session* s) {
+  const dpb200_model* m = s->m;
+  const dpb200_model_config& cfg = m->cfg;
+  Builder b{s, m};
+  const int B = s->B;
+  // ---- geometry (defaults.py:85-89, rcnn.py:174-179)
+  const int mn = s->H0 < s->W0 ? s->H0 : s->W0, mx = s->H0 < s->W0 ? s->W0 : s->H0;
+  const double k1 = (double)cfg.min_size / mn, k2 = (double)cfg.max_size / mx;
+  s->k = k1 < k2 ? k1 : k2;
+  s->Hr = (int)floor((double)s->H0 * s->k);   // F.interpolate: floor(in * scale_factor)
+  s->Wr = (int)floor((double)s->W0 * s->k);
+  s->Hp = round_up(s->Hr, 32); s->Wp = round_up(s->Wr, 32);
+  s->Wx = s->Wp + 16;
+  const int Hp = s->Hp, Wp = s->Wp;
+
+  // ---- a1/a2 preprocess
+  T4 x0 = b.act(B, Hp, s->Wx, 4);
+  b.tap("stem_in", x0);
+  {
+    PreprocessArgs& p = s->pre;
+    p.src = nullptr; p.src_u8 = s->src_u8; p.B = B; p.H0 = s->H0; p.W0 = s->W0; p.Hr = s->Hr; p.Wr = s->Wr;
+    p.inv_scale = (float)(1.0 / s->k);
+    p.flip_rgb = 0;
+    for (int i = 0; i < 3; ++i) { p.mean[i] = cfg.pixel_mean[i]; p.std[i] = cfg.pixel_std[i]; }
+    p.dst = reinterpret_cast<bf16*>(x0.p); p.Hp = Hp; p.Wx = s->Wx;
+    dpb200_session* ss = s;
+    b.op([ss](cudaStream_t st) {
+      PreprocessArgs p = ss->pre;
+      p.src = ss->io->images;
+      p.flip_rgb = (ss->m->cfg.input_rgb && ss->io->bgr) ? 1 : 0;   // defaults.py:82-83
+      return launch_preprocess(p, st);
+    });
+  }
+  // ---- a3 stem: 7x7/2 conv as 7 row taps over a 16-pixel (64-element) sliding window
+  T4 stem = b.act(B, Hp / 2, Wp / 2, 64);
+  {
+    T4 xv = x0; xv.W = Wp / 2; xv.C = 64;   // virtual [B, Hp, Wp/2, 64] view with overlapping windows
+    Builder::ConvOpt o; o.kh = 7; o.kw = 1; o.sy = 2; o.sx = 1; o.pad_y = 3; o.pad_x = 0; o.relu = 1;
+    o.x_sw = 8; o.x_sh = (long long)s->Wx * 4; o.x_sn = (long long)Hp * s->Wx * 4;
+    o.H_out = Hp / 2; o.W_out = Wp / 2;
+    b.conv("backbone.bottom_up.stem.conv1", xv, stem, o);
+  }
+  T4 pool = b.act(B, Hp / 4, Wp / 4, 64);
+  b.op([=](cudaStream_t st) {
+    return launch_maxpool3x3s2((const bf16*)stem.p, (bf16*)pool.p, B, stem.H, stem.W, 64, st);
+  });
+  b.tap("stem_pool", pool);
+
+  // ---- a4 res2..res5
+  const int nblocks[4] = {3, 4, cfg.depth == 101 ? 23 : 6, 3};
+  T4 cur = pool;
+  T4 res_out[4];
+  for (int si = 0; si < 4; ++si) {
+    const int bott = 64 << si, cout = 256 << si;
+    const int stride0 = si > 0 ? 2 : 1;
+    const int H = cur.H / stride0, W = cur.W / stride0;
+    T4 t1 = b.act(B, H, W, bott), t2 = b.act(B, H, W, bott);
+    T4 pp[2] = {b.act(B, H, W, cout), b.act(B, H, W, cout)};
+    T4 sc = b.act(B, H, W, cout);
+    for (int bi = 0; bi < nblocks[si]; ++bi) {
+      const std::string p = "backbone.bottom_up.res" + std::to_string(si + 2) + "." + std::to_string(bi);
+      const int stride = bi == 0 ? stride0 : 1;
+      Builder::ConvOpt o1; o1.k = 1; o1.stride = stride; o1.relu = 1;
+      b.conv(p + ".conv1", cur, t1, o1);
+      Builder::ConvOpt o2; o2.k = 3; o2.pad = 1; o2.relu = 1;
+      b.conv(p + ".conv2", t1, t2, o2);
+      const T4* shortcut = &cur;
+      if (bi == 0) {
+        Builder::ConvOpt os; os.k = 1; os.stride = stride;
+        b.conv(p + ".shortcut", cur, sc, os);
+        shortcut = &sc;
+      }
+      T4 out = pp[bi & 1];
+      Builder::ConvOpt o3; o3.k = 1; o3.relu = 1; o3.res = shortcut;
+      b.conv(p + ".conv3", t2, out, o3);
+      cur = out;
+    }
+    // keep the stage output alive: if it sits in a ping-pong buffer that is fine, the next stage
+    // allocates its own buffers.
+    res_out[si] = cur;
+    b.tap("res" + std::to_string(si + 2), cur);
+  }
+
+  // ---- a5 FPN
+  T4 lat[4], pf[5];
+  for (int l = 3; l >= 0; --l) {
+    lat[l] = b.act(B, res_out[l].H, res_out[l].W, 256);
+    Builder::ConvOpt o; o.k = 1;
+    if (l < 3) { o.res = &lat[l + 1]; o.res_shift = 1; }
+    b.conv("backbone.fpn_lateral" + std::to_string(l + 2), res_out[l], lat[l], o);
+    pf[l] = b.act(B, res_out[l].H, res_out[l].W, 256);
+    Builder::ConvOpt oo; oo.k = 3; oo.pad = 1;
+    b.conv("backbone.fpn_output" + std::to_string(l + 2), lat[l], pf[l], oo);
+    b.tap("p" + std::to_string(l + 2), pf[l]);
+  }
+  // p6 = p5[:, ::2, ::2] (LastLevelMaxPool, fpn.py:199) is only ever read by the RPN conv: strided view.
+  const int H6 = (pf[3].H + 1) / 2, W6 = (pf[3].W + 1) / 2;
+
+  // ---- a7 RPN head
+  T4 rpn_t = b.act(B, pf[0].H, pf[0].W, 256);
+  RpnArgs ra{};
+  T4 rpn_head[5];
+  for (int l = 0; l < 5; ++l) {
+    T4 xin = l < 4 ? pf[l] : pf[3];
+    Builder::ConvOpt o; o.k = 3; o.pad = 1; o.relu = 1;
+    if (l == 4) {
+      xin.H = H6; xin.W = W6;
+      o.x_sw = 2 * 256; o.x_sh = 2LL * pf[3].W * 256; o.x_sn = (long long)pf[3].H * pf[3].W * 256;
+    }
+    T4 t = rpn_t; t.H = xin.H; t.W = xin.W;
+    b.conv("proposal_generator.rpn_head.conv", xin, t, o);
+    rpn_head[l] = b.act(B, xin.H, xin.W, 16, 1);
+    Builder::ConvOpt op; op.k = 1;
+    b.conv("proposal_generator.rpn_head.pred", t, rpn_head[l], op);
+    b.tap("rpn_head" + std::to_string(l), rpn_head[l]);
+    ra.lvl[l].head = (const float*)rpn_head[l].p; ra.lvl[l].H = xin.H; ra.lvl[l].W = xin.W;
+    ra.lvl[l].stride = (float)(4 << l);
+    cell_anchors((float)(32 << l), ra.lvl[l].anchors);
+  }
+  // ---- a8/a9 proposals
+  const int R = cfg.rpn_post_topk, K = cfg.rpn_pre_topk;
+  ra.B = B; ra.pre_topk = K; ra.post_topk = R; ra.nms_thresh = cfg.rpn_nms;
+  ra.clip_x = (float)Hp; ra.clip_y = (float)Wp;     // quirk 1: extents swapped (rpn.py:339 vs structures.py:107-112)
+  ra.cand_boxes = (float*)b.alloc((size_t)B * 5 * K * 16);
+  ra.cand_scores = (float*)b.alloc((size_t)B * 5 * K * 4);
+  ra.cand_count = (int*)b.alloc((size_t)B * 5 * 4);
+  ra.cand_keep = (unsigned char*)b.alloc((size_t)B * 5 * K);
+  ra.prop_boxes = (float*)b.alloc((size_t)B * R * 16);
+  ra.prop_scores = (float*)b.alloc((size_t)B * R * 4);
+  ra.prop_count = (int*)b.alloc((size_t)B * 4);
+  b.tap_raw("proposal_boxes", ra.prop_boxes, B, R, 4, 1, 1);
+  b.tap_raw("proposal_scores", ra.prop_scores, B, R, 1, 1, 1);
+  b.tap_raw("proposal_count", ra.prop_count, B, 1, 1, 1, 2);
+  b.tap_raw("rpn_cand_boxes", ra.cand_boxes, B, 5, K, 4, 1);
+  b.tap_raw("rpn_cand_scores", ra.cand_scores, B, 5, K, 1, 1);
+  b.tap_raw("rpn_cand_keep", ra.cand_keep, B, 5, K, 1, 3);
+  b.op([ra](cudaStream_t st) { return launch_rpn_topk_decode(ra, st); });
+  b.op([ra](cudaStream_t st) { return launch_rpn_nms(ra, st); });
+  b.op([ra](cudaStream_t st) { return launch_rpn_merge(ra, st); });
+
+  // ---- a11-a13 box branch
+  float* rois_box = (float*)b.alloc((size_t)B * R * 5 * 4);
+  b.op([=](cudaStream_t st) { return launch_proposal_rois(ra.prop_boxes, ra.prop_count, B, R, rois_box, st); });
+  T4 box_pooled = b.act(B * R, 7, 7, 256);
+  {
+    RoiAlignArgs a{};
+    for (int l = 0; l < 4; ++l) { a.feat[l] = (const bf16*)pf[l].p; a.H[l] = pf[l].H; a.W[l] = pf[l].W; a.scale[l] = 1.0f / (float)(4 << l); }
+    a.n_levels = 4; a.C = 256; a.rois = rois_box; a.n_rois = nullptr; a.R = B * R; a.P = 7; a.out = box_pooled.p; a.out_fp32 = 0;
+    b.op([a](cudaStream_t st) { return launch_roi_align(a, st); });
+  }
+  b.tap("box_pooled", box_pooled);
+  T4 fc_in = box_pooled; fc_in.H = 1; fc_in.W = 1; fc_in.C = 7 * 7 * 256;
+  T4 fc1 = b.act(B * R, 1, 1, 1024), fc2 = b.act(B * R, 1, 1, 1024), boxpred = b.act(B * R, 1, 1, 16, 1);
+  { Builder::ConvOpt o; o.k = 1; o.relu = 1; b.conv("roi_heads.box_head.fc1", fc_in, fc1, o); }
+  { Builder::ConvOpt o; o.k = 1; o.relu = 1; b.conv("roi_heads.box_head.fc2", fc1, fc2, o); }
+  { Builder::ConvOpt o; o.k = 1; b.conv("roi_heads.box_predictor.pred", fc2, boxpred, o); }
+  b.tap("box_head_out", boxpred);
+  const int topk = cfg.dets_per_image;
+  {
+    BoxPredictArgs& a = s->bp;
+    a.head = (const float*)boxpred.p; a.prop_boxes = ra.prop_boxes; a.prop_count = ra.prop_count;
+    a.B = B; a.R = R; a.score_thresh = cfg.score_thresh; a.nms_thresh = cfg.nms_test; a.topk = topk;
+    // detector_postprocess: scale = out / (image_size - padding)  (postprocessing.py:43-46), fp32 division
+    a.scale_x = (float)s->W0 / (float)s->Wr; a.scale_y = (float)s->H0 / (float)s->Hr;
+    a.out_w = (float)s->W0; a.out_h = (float)s->H0;
+    a.ws_boxes = (float*)b.alloc((size_t)B * 1024 * 16);
+    a.ws_keep = (unsigned char*)b.alloc((size_t)B * 1024);
+    a.det_boxes_raw = (float*)b.alloc((size_t)B * topk * 16);
+    b.tap_raw("det_boxes_raw", a.det_boxes_raw, B, topk, 4, 1, 1);
+    dpb200_session* ss = s;
+    b.op([ss](cudaStream_t st) {
+      BoxPredictArgs a = ss->bp;
+      a.det_boxes = ss->io->pred_boxes; a.det_scores = ss->io->scores; a.det_count = ss->io->det_count;
+      return launch_box_predict(a, st);
+    });
+  }
+  const int Rd = B * topk;
+  s->rois_dp = (float*)b.alloc((size_t)Rd * 5 * 4);
+  s->dp_total = (int*)b.alloc(4);
+  {
+    dpb200_session* ss = s;
+    b.op([ss, B, topk](cudaStream_t st) {
+      return launch_pack_rois(ss->bp.det_boxes_raw, ss->io->det_count, B, topk, ss->rois_dp, ss->dp_total,
+                              ss->io->det_offsets, st);
+    });
+  }
+  b.tap_raw("dp_total", s->dp_total, 1, 1, 1, 1, 2);
+  const int* nv = s->dp_total;
+
+  // ---- a14 decoder
+  T4 dp_feat[4]; int dp_levels = 4;
+  if (cfg.decoder_on) {
+    T4 d2 = b.act(B, pf[0].H, pf[0].W, 256);
+    { Builder::ConvOpt o; o.k = 3; o.pad = 1; o.relu = 1; b.conv("roi_heads.decoder.p2.0", pf[0], d2, o); }
+    T4 branch[3];
+    for (int l = 1; l < 4; ++l) {
+      T4 x = pf[l];
+      for (int kk = 0; kk < l; ++kk) {
+        T4 y = b.act(B, x.H, x.W, 256);
+        Builder::ConvOpt o; o.k = 3; o.pad = 1; o.relu = 1;
+        b.conv("roi_heads.decoder.p" + std::to_string(l + 2) + "." + std::to_string(2 * kk), x, y, o);
+        if (kk != l - 1) {
+          T4 up = b.act(B, y.H * 2, y.W * 2, 256);
+          b.op([=](cudaStream_t st) { return launch_upsample2x((const bf16*)y.p, (bf16*)up.p, B, y.H, y.W, 256, st); });
+          x = up;
+        } else {
+          x = y;   // the last upsample is fused into the merge
+        }
+      }
+      branch[l - 1] = x;
+    }
+    T4 merged = b.act(B, pf[0].H, pf[0].W, 256);
+    b.op([=](cudaStream_t st) {
+      return launch_decoder_merge((const bf16*)d2.p, (const bf16*)branch[0].p, (const bf16*)branch[1].p,
+                                  (const bf16*)branch[2].p, (bf16*)merged.p, B, merged.H, merged.W, 256, st);
+    });
+    T4 dec = b.act(B, pf[0].H, pf[0].W, 256);
+    { Builder::ConvOpt o; o.k = 1; b.conv("roi_heads.decoder.predictor", merged, dec, o); }
+    b.tap("decoder", dec);
+    dp_feat[0] = dec; dp_levels = 1;
+  } else {
+    for (int l = 0; l < 4; ++l) dp_feat[l] = pf[l];
+  }
+  // ---- a11 (DensePose pooler)
+  const int P = cfg.pooler_res;
+  T4 dp_pooled = b.act(Rd, P, P, 256);
+  {
+    RoiAlignArgs a{};
+    for (int l = 0; l < dp_levels; ++l) { a.feat[l] = (const bf16*)dp_feat[l].p; a.H[l] = dp_feat[l].H; a.W[l] = dp_feat[l].W; a.scale[l] = 1.0f / (float)(4 << l); }
+    a.n_levels = dp_levels; a.C = 256; a.rois = s->rois_dp; a.n_rois = nv; a.R = Rd; a.P = P; a.out = dp_pooled.p;
+    b.op([a](cudaStream_t st) { return launch_roi_align(a, st); });
+  }
+  b.tap("dp_pooled", dp_pooled);
+  // ---- a16/a17 head
+  T4 hb[2] = {b.act(Rd, P, P, 512), b.act(Rd, P, P, 512)};
+  T4 head_out;
+  const std::string hp = "roi_heads.densepose_head.";
+  if (cfg.head == 0) {
+    T4 x = dp_pooled;
+    for (int i = 0; i < 8; ++i) {
+      Builder::ConvOpt o; o.k = 3; o.pad = 1; o.relu = 1; o.n_valid = nv;
+      b.conv(hp + "body_conv_fcn" + std::to_string(i + 1), x, hb[i & 1], o);
+      x = hb[i & 1];
+    }
+    head_out = x;
+  } else {
+    const int HW = P * P;
+    T4 cat = b.act(Rd, P, P, 1280);
+    T4 tmp = b.act(Rd, P, P, 512);
+    T4 tmp256 = tmp; tmp256.C = 256;
+    auto gn = [&](const std::string& name, const T4& x, bf16* y, int ycs, int hw_in, int hw_out) {
+      const Weight* w = b.weight(name);
+      if (!w) return;
+      const float* g = (const float*)w->d0; const float* be = (const float*)w->d1;
+      const bf16* xp = (const bf16*)x.p; const int C = x.C; const int R_ = Rd;
+      b.op([=](cudaStream_t st) { return launch_groupnorm_relu(xp, g, be, y, R_, hw_in, C, ycs, hw_out, nv, st); });
+    };
+    // ASPP branches (deeplab.py:112-144); branch 3 (rate 56 >= P) only ever sees its centre tap
+    const int dil[3] = {1, 6, 12};
+    for (int i = 0; i < 3; ++i) {
+      Builder::ConvOpt o; o.k = i == 0 ? 1 : 3; o.dil = dil[i]; o.pad = i == 0 ? 0 : dil[i]; o.n_valid = nv; o.no_bias = true;
+      b.conv(hp + "ASPP.convs." + std::to_string(i) + ".0", dp_pooled, tmp256, o);
+      gn(hp + "ASPP.convs." + std::to_string(i) + ".1", tmp256, (bf16*)cat.p + 256 * i, 1280, HW, HW);
+    }
+    { Builder::ConvOpt o; o.k = 1; o.n_valid = nv; o.no_bias = true;
+      b.conv(hp + "ASPP.convs.3.0", dp_pooled, tmp256, o);
+      gn(hp + "ASPP.convs.3.1", tmp256, (bf16*)cat.p + 768, 1280, HW, HW); }
+    T4 pooled = b.act(Rd, 1, 1, 256), pooled_c = b.act(Rd, 1, 1, 256);
+    b.op([=](cudaStream_t st) { return launch_avgpool((const bf16*)dp_pooled.p, (bf16*)pooled.p, Rd, HW, 256, nv, st); });
+    { Builder::ConvOpt o; o.k = 1; o.n_valid = nv; o.no_bias = true; b.conv(hp + "ASPP.convs.4.1", pooled, pooled_c, o); }
+    gn(hp + "ASPP.convs.4.2", pooled_c, (bf16*)cat.p + 1024, 1280, 1, HW);
+    T4 proj = b.act(Rd, P, P, 256);
+    { Builder::ConvOpt o; o.k = 1; o.relu = 1; o.n_valid = nv; o.no_bias = true; b.conv(hp + "ASPP.project.0", cat, proj, o); }
+    T4 x = proj;
+    for (int i = 0; i < 8; ++i) {
+      const std::string name = hp + "body_conv_fcn" + std::to_string(i + 1);
+      Builder::ConvOpt o; o.k = 3; o.pad = 1; o.n_valid = nv; o.no_bias = true;
+      b.conv(name, x, tmp, o);
+      gn(name + ".norm", tmp, (bf16*)hb[i & 1].p, 512, HW, HW);
+      x = hb[i & 1];
+    }
+    head_out = x;
+  }
+  b.tap("dp_head", head_out);
+  // ---- a18 predictor: ConvTranspose2d(k4,s2,p1) as four 2x2 phase convs, then bilinear x2 -> NCHW fp32
+  const int Cp = round_up(cfg.coarse_ch + 75, 16);
+  const int S2 = 2 * P;
+  T4 low = b.act(Rd, S2, S2, Cp, 1);
+  s->low = (float*)low.p; s->low_S = S2; s->low_C = Cp;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      Builder::ConvOpt o; o.k = 2; o.pad_y = py == 0 ? 1 : 0; o.pad_x = px == 0 ? 1 : 0; o.n_valid = nv;
+      o.H_out = P; o.W_out = P;
+      o.out_sx = 2LL * Cp; o.out_sy = 2LL * S2 * Cp; o.out_sn = (long long)S2 * S2 * Cp;
+      o.out_off = ((long long)py * S2 + px) * Cp;
+      b.conv("roi_heads.densepose_predictor.phase" + std::to_string(py * 2 + px), head_out, low, o);
+    }
+  b.tap("dp_lowres", low);
+  {
+    dpb200_session* ss = s;
+    const int Kc = cfg.coarse_ch;
+    b.op([ss, Rd, Kc, nv](cudaStream_t st) {
+      return launch_predictor_upsample(ss->low, Rd, ss->low_S, ss->low_C, Kc, nv, ss->io->coarse, ss->io->fine,
+                                       ss->io->u, ss->io->v, st);
+    });
+  }
+  return b.fail;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dpb200_model_create(const dpb200_model_config* cfg, const dpb200_weight* w, int32_t n, dpb200_model** out) {
+  if (!cfg || !w || !out) { set_error("model_create: null argument"); return -1; }
+  if (cfg->depth != 50 && cfg->depth != 101) { set_error("model_create: depth %d unsupported", cfg->depth); return -1; }
+  if (cfg->rpn_pre_topk > 1024 || cfg->rpn_post_topk > 1024 || cfg->dets_per_image > 1024) {
+    set_error("model_create: top-k limits above 1024 unsupported"); return -1;
+  }
+  dpb200_model* m = new dpb200_model();
+  m->cfg = *cfg;
+  for (int i = 0; i < n; ++i) m->w[w[i].name] = Weight{w[i].data0, w[i].data1, w[i].cin_pad, w[i].cout_pad};
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (m->num_sms <= 0) m->num_sms = 148;
+  *out = m;
+  return 0;
+}
+void dpb200_model_destroy(dpb200_model* m) { delete m; }
+
+size_t dpb200_session_workspace_bytes(const dpb200_model* m, int32_t b, int32_t h0, int32_t w0) {
+  dpb200_session s;
+  s.m = m; s.B = b; s.H0 = h0; s.W0 = w0; s.dry = true;
+  if (build_plan(&s)) return 0;
+  return s.ws_used + 4096;
+}
+
+int dpb200_session_create(const dpb200_model* m, int32_t b, int32_t h0, int32_t w0, int32_t src_u8,
+                          void* workspace, size_t workspace_bytes, dpb200_session** out) {
+  if (!m || !workspace || !out) { set_error("session_create: null argument"); return -1; }
+  dpb200_session* s = new dpb200_session();
+  s->m = m; s->B = b; s->H0 = h0; s->W0 = w0; s->src_u8 = src_u8;
+  s->ws = reinterpret_cast<char*>(workspace); s->ws_bytes = workspace_bytes;
+  int r = build_plan(s);
+  if (r) { delete s; return r; }
+  *out = s;
+  return 0;
+}
+void dpb200_session_destroy(dpb200_session* s) { delete s; }
+
+int dpb200_session_run(dpb200_session* s, const dpb200_forward_io* io, void* stream) {
+  if (!s || !io) { set_error("session_run: null argument"); return -1; }
+  s->io = io;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (auto& f : s->ops) {
+    int r = f(st);
+    if (r) return r;
+  }
+  return 0;
+}
+
+int dpb200_session_launch_count(const dpb200_session* s) { return s ? (int)s->ops.size() : 0; }
+double dpb200_session_flops(const dpb200_session* s) { return s ? s->flops : 0.0; }
+void dpb200_session_geometry(const dpb200_session* s, int32_t out[4]) {
+  out[0] = s->Hr; out[1] = s->Wr; out[2] = s->Hp; out[3] = s->Wp;
+}
+int dpb200_session_tap(const dpb200_session* s, const char* name, void** ptr, int64_t shape[4], int32_t* dtype) {
+  auto it = s->taps.find(name);
+  if (it == s->taps.end()) { set_error("tap: unknown tensor '%s'", name); return -1; }
+  *ptr = it->second.p;
+  for (int i = 0; i < 4; ++i) shape[i] = it->second.shape[i];
+  *dtype = it->second.dtype;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+// ROIAlign over the FPN pyramid, and the box-head tail (softmax, decode, threshold, NMS, top-k,
+// detector_postprocess) — all on the device with device-side counts, no host sync.
+// Reference: poolers.py:15-51,187-227; layers/roi_align.py:49-65 (-> torchvision roi_align, aligned=False);
+// fast_rcnn.py:86-140,257-326; postprocessing.py:11-61; structures.py:107-140.
+#include "kernels.cuh"
+#include "conv_igemm.cuh"
+#include "device_utils.cuh"
+#include "ptx.cuh"
+
+namespace dpb {
+
+#define DPB_CHECK_LAUNCH(name)                                                     \
+  do {                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                          \
+    if (e__ != cudaSuccess) {                                                      \
+      set_error("%s launch: %s", name, cudaGetErrorString(e__));                   \
+      return -4;                                                                   \
+    }                                                                              \
+  } while (0)
+
+
+// ------------------------------------------------------------------------------------ ROIAlign
+struct Tap {
+  int lo, hi;
+  float l, h;
+  bool dead;
+};
+// torchvision bilinear pre-calc for one coordinate (aligned=False)
+__device__ __forceinline__ Tap make_tap(float v, int size) {
+  Tap t;
+  t.dead = (v < -1.0f) || (v > (float)size);
+  if (v <= 0.f) v = 0.f;
+  int lo = (int)v;
+  int hi;
+  if (lo >= size - 1) { hi = lo = size - 1; v = (float)lo; }
+  else hi = lo + 1;
+  t.lo = lo; t.hi = hi;
+  t.l = __fsub_rn(v, (float)lo);
+  t.h = __fsub_rn(1.f, t.l);
+  return t;
+}
+
+__global__ void __launch_bounds__(256) roi_align_kernel(RoiAlignArgs a) {
+  const int r = blockIdx.x;
+  if (a.n_rois != nullptr && r >= *a.n_rois) return;
+  const float* roi = a.rois + (long long)r * 5;
+  const int b = (int)roi[0];
+  const float x1 = roi[1], y1 = roi[2], x2 = roi[3], y2 = roi[4];
+  int lvl = 0;
+  if (a.n_levels > 1) {
+    // poolers.py:43-51: floor(4 + log2(sqrt(area)/224 + 1e-8)) clamped to [2, 5]
+    const float area = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+    const float v = __fadd_rn(__fdiv_rn(sqrtf(area), 224.f), 1e-8f);
+    float l = floorf(__fadd_rn(4.f, log2f(v)));
+    l = fminf(fmaxf(l, 2.f), 5.f);
+    lvl = (int)l - 2;
+    if (lvl >= a.n_levels) lvl = a.n_levels - 1;
+  }
+  const int H = a.H[lvl], W = a.W[lvl];
+  const float scale = a.scale[lvl];
+  const int C8 = a.C / 8;
+  const uint4* feat = reinterpret_cast<const uint4*>(a.feat[lvl]) + (long long)b * H * W * C8;
+  const int P = a.P;
+  const float fx0 = __fmul_rn(x1, scale), fy0 = __fmul_rn(y1, scale);
+  const float rw = fmaxf(__fsub_rn(__fmul_rn(x2, scale), fx0), 1.f);
+  const float rh = fmaxf(__fsub_rn(__fmul_rn(y2, scale), fy0), 1.f);
+  const float bw = __fdiv_rn(rw, (float)P), bh = __fdiv_rn(rh, (float)P);
+
+  const int chunk = threadIdx.x % C8;
+  const int group = threadIdx.x / C8, groups = blockDim.x / C8;
+  for (int bin = group; bin < P * P; bin += groups) {
+    const int ph = bin / P, pw = bin - ph * P;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy) {
+      const float yy = __fadd_rn(__fadd_rn(fy0, __fmul_rn((float)ph, bh)),
+                                 __fdiv_rn(__fmul_rn((float)iy + 0.5f, bh), 2.f));
+      const Tap ty = make_tap(yy, H);
+#pragma unroll
+      for (int ix = 0; ix < 2; ++ix) {
+        const float xx = __fadd_rn(__fadd_rn(fx0, __fmul_rn((float)pw, bw)),
+                                   __fdiv_rn(__fmul_rn((float)ix + 0.5f, bw), 2.f));
+        const Tap tx = make_tap(xx, W);
+        if (ty.dead || tx.dead) continue;
+        const float w1 = __fmul_rn(ty.h, tx.h), w2 = __fmul_rn(ty.h, tx.l);
+        const float w3 = __fmul_rn(ty.l, tx.h), w4 = __fmul_rn(ty.l, tx.l);
+        float v1[8], v2[8], v3[8], v4[8];
+        const uint4 q1 = __ldg(feat + ((long long)ty.lo * W + tx.lo) * C8 + chunk);
+        const uint4 q2 = __ldg(feat + ((long long)ty.lo * W + tx.hi) * C8 + chunk);
+        const uint4 q3 = __ldg(feat + ((long long)ty.hi * W + tx.lo) * C8 + chunk);
+        const uint4 q4 = __ldg(feat + ((long long)ty.hi * W + tx.hi) * C8 + chunk);
+        v1[0] = bf16_lo(q1.x); v1[1] = bf16_hi(q1.x); v1[2] = bf16_lo(q1.y); v1[3] = bf16_hi(q1.y);
+        v1[4] = bf16_lo(q1.z); v1[5] = bf16_hi(q1.z); v1[6] = bf16_lo(q1.w); v1[7] = bf16_hi(q1.w);
+        v2[0] = bf16_lo(q2.x); v2[1] = bf16_hi(q2.x); v2[2] = bf16_lo(q2.y); v2[3] = bf16_hi(q2.y);
+        v2[4] = bf16_lo(q2.z); v2[5] = bf16_hi(q2.z); v2[6] = bf16_lo(q2.w); v2[7] = bf16_hi(q2.w);
+        v3[0] = bf16_lo(q3.x); v3[1] = bf16_hi(q3.x); v3[2] = bf16_lo(q3.y); v3[3] = bf16_hi(q3.y);
+        v3[4] = bf16_lo(q3.z); v3[5] = bf16_hi(q3.z); v3[6] = bf16_lo(q3.w); v3[7] = bf16_hi(q3.w);
+        v4[0] = bf16_lo(q4.x); v4[1] = bf16_hi(q4.x); v4[2] = bf16_lo(q4.y); v4[3] = bf16_hi(q4.y);
+        v4[4] = bf16_lo(q4.z); v4[5] = bf16_hi(q4.z); v4[6] = bf16_lo(q4.w); v4[7] = bf16_hi(q4.w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // output_val += w1*v1 + w2*v2 + w3*v3 + w4*v4, each product and sum rounded (no FMA)
+          const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1[i]), __fmul_rn(w2, v2[i])),
+                                              __fmul_rn(w3, v3[i])),
+                                    __fmul_rn(w4, v4[i]));
+          acc[i] = __fadd_rn(acc[i], s);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = __fdiv_rn(acc[i], 4.f);
+    const long long o = ((long long)r * P * P + bin) * a.C + chunk * 8;
+    if (a.out_fp32) {
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + o);
+      dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+      uint4 v;
+      v.x = pack_bf16(acc[0], acc[1]); v.y = pack_bf16(acc[2], acc[3]);
+      v.z = pack_bf16(acc[4], acc[5]); v.w = pack_bf16(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.out) + o) = v;
+    }
+  }
+}
+
+int launch_roi_align(const RoiAlignArgs& a, cudaStream_t s) {
+  if (a.C % 8 || 256 % (a.C / 8)) { set_error("roi_align: C/8 must divide 256"); return -1; }
+  if (a.R == 0) return 0;
+  roi_align_kernel<<<a.R, 256, 0, s>>>(a);
+  DPB_CHECK_LAUNCH("roi_align");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ box predictor tail
+
+__global__ void __launch_bounds__(1024)
+box_predict_kernel(BoxPredictArgs a) {
+  extern __shared__ uint32_t bp_smem[];
+  // layout: [nms region (kNms)] [keys 1024 u64] [boxes 1024 float4] [scores 1024 f32]
+  const int kNms = 1024 * 32 * 4 + 1024 * 16 + 1024 * 4 + 32 * 4;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(bp_smem) + kNms);
+  float4* sbox = reinterpret_cast<float4*>(keys + 1024);
+  float* sscore = reinterpret_cast<float*>(sbox + 1024);
+  __shared__ unsigned s_ncand, s_warp[32], s_total;
+  const int b = blockIdx.x, t = threadIdx.x;
+  if (t == 0) s_ncand = 0;
+  __syncthreads();
+  const int np = a.prop_count[b] < a.R ? a.prop_count[b] : a.R;
+  unsigned long long key = 0ull;
+  if (t < np) {
+    const float* h = a.head + ((long long)b * a.R + t) * 16;
+    const float l0 = h[0], l1 = h[1];
+    // F.softmax(dim=-1): exp(x - max) / sum  (fast_rcnn.py:325)
+    const float m = fmaxf(l0, l1);
+    const float e0 = expf(__fsub_rn(l0, m)), e1 = expf(__fsub_rn(l1, m));
+    const float sum = __fadd_rn(e0, e1);
+    const float p0 = __fdiv_rn(e0, sum), p1 = __fdiv_rn(e1, sum);
+    const float4 pb = reinterpret_cast<const float4*>(a.prop_boxes)[(long long)b * a.R + t];
+    float d[4] = {h[2], h[3], h[4], h[5]}, box[4];
+    // Box2BoxTransform weights (10, 10, 5, 5): fast_rcnn.py:300-303
+    {
+      const float scale_clamp = 4.135166556742356f;
+      const float widths = __fsub_rn(pb.z, pb.x), heights = __fsub_rn(pb.w, pb.y);
+      const float ctr_x = __fadd_rn(pb.x, __fmul_rn(0.5f, widths));
+      const float ctr_y = __fadd_rn(pb.y, __fmul_rn(0.5f, heights));
+      const float dx = __fdiv_rn(d[0], 10.f), dy = __fdiv_rn(d[1], 10.f);
+      const float dw = fminf(__fdiv_rn(d[2], 5.f), scale_clamp), dh = fminf(__fdiv_rn(d[3], 5.f), scale_clamp);
+      const float pcx = __fadd_rn(__fmul_rn(dx, widths), ctr_x);
+      const float pcy = __fadd_rn(__fmul_rn(dy, heights), ctr_y);
+      const float pw = __fmul_rn(expf(dw), widths), ph = __fmul_rn(expf(dh), heights);
+      box[0] = __fsub_rn(pcx, __fmul_rn(0.5f, pw)); box[1] = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+      box[2] = __fadd_rn(pcx, __fmul_rn(0.5f, pw)); box[3] = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+    }
+    const bool finite = isfinite(box[0]) && isfinite(box[1]) && isfinite(box[2]) && isfinite(box[3]) &&
+                        isfinite(p0) && isfinite(p1);
+    sbox[t] = make_float4(box[0], box[1], box[2], box[3]);
+    sscore[t] = p0;
+    if (finite && p0 > a.score_thresh) {   // fast_rcnn.py:105-118 (clip at :113 is a discarded no-op)
+      key = ((unsigned long long)f2ord(p0) << 32) | (0xFFFFFFFFu - (uint32_t)t);
+      atomicAdd(&s_ncand, 1u);
+    }
+  }
+  keys[t] = key;
+  __syncthreads();
+  bitonic_sort_desc(keys, 1024);
+  const int ncand = (int)s_ncand;
+  float4* gb = reinterpret_cast<float4*>(a.ws_boxes) + (long long)b * 1024;
+  unsigned char* gk = a.ws_keep + (long long)b * 1024;
+  int src = -1;
+  if (t < ncand) {
+    src = (int)(0xFFFFFFFFu - (uint32_t)(keys[t] & 0xFFFFFFFFull));
+    gb[t] = sbox[src];
+    gk[t] = 1;
+  } else {
+    gk[t] = 0;
+  }
+  __syncthreads();
+  nms_sorted_block(gb, ncand, a.nms_thresh, gk, bp_smem);   // batched_nms with a single class
+  __syncthreads();
+  // first `topk` kept, in score order
+  const unsigned flag = (t < ncand && gk[t]) ? 1u : 0u;
+  unsigned incl = flag;
+  {
+    const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += v;
+      }
+      s_warp[lane] = w;
+      if (lane == 31) s_total = w;
+    }
+    __syncthreads();
+    if (warp > 0) incl += s_warp[warp - 1];
+  }
+  const int pos = (int)incl - 1;
+  if (flag && pos < a.topk) {
+    const float4 bx = sbox[src];
+    const long long o = (long long)b * a.topk + pos;
+    reinterpret_cast<float4*>(a.det_boxes_raw)[o] = bx;
+    // detector_postprocess: scale_boxes then clip to (H_orig, W_orig)  (postprocessing.py:43-54)
+    float4 ob;
+    ob.x = fminf(fmaxf(__fmul_rn(bx.x, a.scale_x), 0.f), a.out_w);
+    ob.y = fminf(fmaxf(__fmul_rn(bx.y, a.scale_y), 0.f), a.out_h);
+    ob.z = fminf(fmaxf(__fmul_rn(bx.z, a.scale_x), 0.f), a.out_w);
+    ob.w = fminf(fmaxf(__fmul_rn(bx.w, a.scale_y), 0.f), a.out_h);
+    reinterpret_cast<float4*>(a.det_boxes)[o] = ob;
+    a.det_scores[o] = sscore[src];
+  }
+  if (t == 0) a.det_count[b] = (int)s_total < a.topk ? (int)s_total : a.topk;
+}
+
+static constexpr int kBoxPredictSmem = (1024 * 32 * 4 + 1024 * 16 + 1024 * 4 + 32 * 4) + 1024 * 8 + 1024 * 16 + 1024 * 4;
+
+int launch_box_predict(const BoxPredictArgs& a, cudaStream_t s) {
+  if (a.R > 1024) { set_error("box_predict: R > 1024"); return -1; }
+  static bool once = false;
+  if (!once) {
+    cudaError_t e = cudaFuncSetAttribute(box_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kBoxPredictSmem);
+    if (e != cudaSuccess) { set_error("box_predict smem: %s", cudaGetErrorString(e)); return -3; }
+    once = true;
+  }
+  box_predict_kernel<<<a.B, 1024, kBoxPredictSmem, s>>>(a);
+  DPB_CHECK_LAUNCH("box_predict");
+  return 0;
+}
+
+__global__ void pack_rois_kernel(const float4* __restrict__ boxes, const int* __restrict__ count, int B,
+                                 int topk, float* __restrict__ rois, int* __restrict__ total,
+                                 int* __restrict__ offsets) {
+  __shared__ int s_off[1025];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < B; ++b) { s_off[b] = acc; acc += count[b]; }
+    s_off[B] = acc;
+    *total = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= B; i += blockDim.x) offsets[i] = s_off[i];
+  for (int i = threadIdx.x; i < B * topk; i += blockDim.x) {
+    const int b = i / topk, t = i - b * topk;
+    if (t < count[b]) {
+      const float4 bx = boxes[i];
+      float* o = rois + (long long)(s_off[b] + t) * 5;
+      o[0] = (float)b; o[1] = bx.x; o[2] = bx.y; o[3] = bx.z; o[4] = bx.w;
+    }
+  }
+}
+
+int launch_pack_rois(const float* det_boxes_raw, const int* det_count, int B, int topk, float* rois,
+                     int* total, int* offsets, cudaStream_t s) {
+  if (B > 1024) { set_error("pack_rois: B > 1024"); return -1; }
+  pack_rois_kernel<<<1, 256, 0, s>>>(reinterpret_cast<const float4*>(det_boxes_raw), det_count, B, topk,
+                                     rois, total, offsets);
+  DPB_CHECK_LAUNCH("pack_rois");
+  return 0;
+}
+
+__global__ void proposal_rois_kernel(const float4* __restrict__ boxes, const int* __restrict__ count, int B,
+                                     int R, float* __restrict__ rois) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * R; i += gridDim.x * blockDim.x) {
+    const int b = i / R, t = i - b * R;
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < count[b]) bx = boxes[i];
+    float* o = rois + (long long)i * 5;
+    o[0] = (float)b; o[1] = bx.x; o[2] = bx.y; o[3] = bx.z; o[4] = bx.w;
+  }
+}
+
+int launch_proposal_rois(const float* prop_boxes, const int* prop_count, int B, int R, float* rois,
+                         cudaStream_t s) {
+  const int g = (B * R + 255) / 256;
+  proposal_rois_kernel<<<g, 256, 0, s>>>(reinterpret_cast<const float4*>(prop_boxes), prop_count, B, R, rois);
+  DPB_CHECK_LAUNCH("proposal_rois");
+  return 0;
+}
+
+}  // namespace dpb

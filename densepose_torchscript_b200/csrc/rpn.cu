@@ -1,0 +1,256 @@
+// RPN proposal selection on the device, no host sync:
+//   rpn_topk_decode : per (image, level) exact top-k of the objectness logits (radix select + bitonic
+//                     sort), anchor generation + Box2BoxTransform.apply_deltas for the selected anchors
+//                     only, (swapped-extent) clip, finite / non-empty flags.
+//   rpn_nms         : per (image, level) greedy NMS (IoU bit-mask in shared memory + warp scan).
+//   rpn_merge       : per image merge of the kept candidates, sort by score, first post_topk.
+// Reference: proposal_generator/rpn.py:319-394, proposal_utils.py:19-134, box_regression.py:74-112,
+// anchor_generator.py:165-231, structures.py:107-122; torchvision nms semantics.
+#include "kernels.cuh"
+#include "conv_igemm.cuh"
+#include "device_utils.cuh"
+
+#include <math.h>
+
+namespace dpb {
+
+#define DPB_CHECK_LAUNCH(name)                                                     \
+  do {                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                          \
+    if (e__ != cudaSuccess) {                                                      \
+      set_error("%s launch: %s", name, cudaGetErrorString(e__));                   \
+      return -4;                                                                   \
+    }                                                                              \
+  } while (0)
+
+__device__ __forceinline__ void decode_box(const float* __restrict__ d, float ax1, float ay1, float ax2,
+                                           float ay2, float wx, float wy, float ww, float wh,
+                                           float* out) {
+  // box_regression.py:86-110, every operation rounded separately (no FMA) like the eager reference
+  const float scale_clamp = 4.135166556742356f;   // log(1000/16)
+  const float widths = __fsub_rn(ax2, ax1), heights = __fsub_rn(ay2, ay1);
+  const float ctr_x = __fadd_rn(ax1, __fmul_rn(0.5f, widths));
+  const float ctr_y = __fadd_rn(ay1, __fmul_rn(0.5f, heights));
+  const float dx = __fdiv_rn(d[0], wx), dy = __fdiv_rn(d[1], wy);
+  float dw = __fdiv_rn(d[2], ww), dh = __fdiv_rn(d[3], wh);
+  dw = fminf(dw, scale_clamp);
+  dh = fminf(dh, scale_clamp);
+  const float pcx = __fadd_rn(__fmul_rn(dx, widths), ctr_x);
+  const float pcy = __fadd_rn(__fmul_rn(dy, heights), ctr_y);
+  const float pw = __fmul_rn(expf(dw), widths);
+  const float ph = __fmul_rn(expf(dh), heights);
+  out[0] = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+  out[1] = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+  out[2] = __fadd_rn(pcx, __fmul_rn(0.5f, pw));
+  out[3] = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+}
+
+__global__ void __launch_bounds__(1024)
+rpn_topk_decode_kernel(RpnArgs a) {
+  const int lvl = blockIdx.x, b = blockIdx.y;
+  const RpnLevel& L = a.lvl[lvl];
+  const int n = L.H * L.W * 3;
+  const int k = n < a.pre_topk ? n : a.pre_topk;
+  const float* head = L.head + (long long)b * L.H * L.W * 16;
+
+  __shared__ unsigned hist[2048];
+  __shared__ unsigned warp_sums[32];
+  __shared__ unsigned long long keys[1024];
+  __shared__ unsigned s_bin, s_above, s_cnt, s_eq_taken;
+
+  auto key_at = [&](int i) -> uint32_t { return f2ord(__ldg(head + (long long)(i / 3) * 16 + (i % 3))); };
+
+  uint32_t prefix = 0, mask = 0;
+  unsigned remaining = (unsigned)k;
+  const int shifts[3] = {21, 10, 0};
+  const int bits[3] = {11, 11, 10};
+  for (int pass = 0; pass < 3; ++pass) {
+    const int nb = 1 << bits[pass];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t u = key_at(i);
+      if ((u & mask) == prefix) atomicAdd(&hist[(u >> shifts[pass]) & (nb - 1)], 1u);
+    }
+    __syncthreads();
+    // reversed bins: thread t owns reversed positions 2t, 2t+1 (bin = nb-1-pos)
+    unsigned c0 = 0, c1 = 0;
+    const int p0 = 2 * threadIdx.x, p1 = p0 + 1;
+    if (p0 < nb) c0 = hist[nb - 1 - p0];
+    if (p1 < nb) c1 = hist[nb - 1 - p1];
+    const unsigned incl = block_scan_incl(c0 + c1, warp_sums);
+    const unsigned before = incl - (c0 + c1);
+    if (before < remaining && remaining <= incl) {
+      if (remaining <= before + c0) { s_bin = nb - 1 - p0; s_above = before; }
+      else { s_bin = nb - 1 - p1; s_above = before + c0; }
+    }
+    __syncthreads();
+    prefix |= (s_bin << shifts[pass]);
+    mask |= ((uint32_t)(nb - 1) << shifts[pass]);
+    remaining -= s_above;
+    __syncthreads();
+  }
+  // prefix == k-th largest key T; `remaining` of the elements equal to T are needed.
+  const uint32_t T = prefix;
+  const unsigned eq_total = hist[T & 1023u];
+  if (threadIdx.x == 0) { s_cnt = 0; s_eq_taken = 0; }
+  keys[threadIdx.x] = 0ull;
+  __syncthreads();
+  const bool take_all_eq = (eq_total == remaining);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t u = key_at(i);
+    if (u > T || (take_all_eq && u == T)) {
+      const unsigned pos = atomicAdd(&s_cnt, 1u);
+      if (pos < 1024) keys[pos] = ((unsigned long long)u << 32) | (0xFFFFFFFFu - (uint32_t)i);
+    }
+  }
+  __syncthreads();
+  if (!take_all_eq) {
+    // excess ties: keep the lowest-index ones, chunk by chunk in index order
+    for (int base = 0; base < n; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      const unsigned flag = (i < n && key_at(i) == T) ? 1u : 0u;
+      const unsigned incl = block_scan_incl(flag, warp_sums);
+      const unsigned taken = s_eq_taken;
+      if (flag && taken + incl <= remaining) {
+        const unsigned pos = atomicAdd(&s_cnt, 1u);
+        if (pos < 1024) keys[pos] = ((unsigned long long)T << 32) | (0xFFFFFFFFu - (uint32_t)i);
+      }
+      __syncthreads();
+      if (threadIdx.x == blockDim.x - 1) s_eq_taken = taken + incl;
+      __syncthreads();
+      if (s_eq_taken >= remaining) break;
+    }
+  }
+  __syncthreads();
+  bitonic_sort_desc(keys, 1024);
+
+  const int t = threadIdx.x;
+  const long long slot = ((long long)b * 5 + lvl) * a.pre_topk + t;
+  if (t < k) {
+    const unsigned long long key = keys[t];
+    const float score = ord2f((uint32_t)(key >> 32));
+    const int i = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+    const int an = i % 3, pix = i / 3;
+    const int x = pix % L.W, y = pix / L.W;
+    const float sx = (float)x * L.stride, sy = (float)y * L.stride;
+    const float ax1 = __fadd_rn(sx, L.anchors[an * 4 + 0]), ay1 = __fadd_rn(sy, L.anchors[an * 4 + 1]);
+    const float ax2 = __fadd_rn(sx, L.anchors[an * 4 + 2]), ay2 = __fadd_rn(sy, L.anchors[an * 4 + 3]);
+    float d[4], box[4];
+    // deltas live at channels 3 + an*4 .. +3 (not 16-byte aligned): scalar loads
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[j] = __ldg(head + (long long)pix * 16 + 3 + an * 4 + j);
+    decode_box(d, ax1, ay1, ax2, ay2, 1.f, 1.f, 1.f, 1.f, box);
+    const bool finite = isfinite(box[0]) && isfinite(box[1]) && isfinite(box[2]) && isfinite(box[3]) &&
+                        isfinite(score);
+    // clip_boxes(boxes, image_size) with image_size = (W_pad, H_pad): x in [0, H_pad], y in [0, W_pad]
+    box[0] = fminf(fmaxf(box[0], 0.f), a.clip_x);
+    box[1] = fminf(fmaxf(box[1], 0.f), a.clip_y);
+    box[2] = fminf(fmaxf(box[2], 0.f), a.clip_x);
+    box[3] = fminf(fmaxf(box[3], 0.f), a.clip_y);
+    const bool nonempty = (__fsub_rn(box[2], box[0]) >= 0.f) && (__fsub_rn(box[3], box[1]) >= 0.f);
+    reinterpret_cast<float4*>(a.cand_boxes)[slot] = make_float4(box[0], box[1], box[2], box[3]);
+    a.cand_scores[slot] = score;
+    a.cand_keep[slot] = (finite && nonempty) ? 1 : 0;
+  } else if (t < a.pre_topk) {
+    a.cand_keep[slot] = 0;
+  }
+  if (t == 0) a.cand_count[b * 5 + lvl] = k;
+}
+
+int launch_rpn_topk_decode(const RpnArgs& a, cudaStream_t s) {
+  if (a.pre_topk > 1024) { set_error("rpn: pre_topk > 1024 unsupported"); return -1; }
+  dim3 grid(5, a.B);
+  rpn_topk_decode_kernel<<<grid, 1024, 0, s>>>(a);
+  DPB_CHECK_LAUNCH("rpn_topk_decode");
+  return 0;
+}
+
+static constexpr int kNmsSmem = 1024 * 32 * 4 + 1024 * 16 + 1024 * 4 + 32 * 4;
+
+__global__ void __launch_bounds__(1024) rpn_nms_kernel(RpnArgs a) {
+  extern __shared__ uint32_t nms_smem[];
+  const int lvl = blockIdx.x, b = blockIdx.y;
+  const int n = a.cand_count[b * 5 + lvl];
+  const long long base = ((long long)b * 5 + lvl) * a.pre_topk;
+  nms_sorted_block(reinterpret_cast<const float4*>(a.cand_boxes) + base, n, a.nms_thresh,
+                   a.cand_keep + base, nms_smem);
+}
+
+__global__ void __launch_bounds__(1024)
+nms_sorted_kernel(const float4* boxes, int n, float thr, unsigned char* keep) {
+  extern __shared__ uint32_t nms_smem[];
+  nms_sorted_block(boxes, n, thr, keep, nms_smem);
+}
+
+static int ensure_smem(const void* fn, int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return -3; }
+  return 0;
+}
+
+int launch_rpn_nms(const RpnArgs& a, cudaStream_t s) {
+  static bool once = false;
+  if (!once) { if (ensure_smem((const void*)rpn_nms_kernel, kNmsSmem)) return -3; once = true; }
+  dim3 grid(5, a.B);
+  rpn_nms_kernel<<<grid, 1024, kNmsSmem, s>>>(a);
+  DPB_CHECK_LAUNCH("rpn_nms");
+  return 0;
+}
+
+int launch_nms_sorted(const float* boxes, int n, float thr, unsigned char* keep, cudaStream_t s) {
+  if (n > 1024) { set_error("nms_sorted: n > 1024"); return -1; }
+  static bool once = false;
+  if (!once) { if (ensure_smem((const void*)nms_sorted_kernel, kNmsSmem)) return -3; once = true; }
+  nms_sorted_kernel<<<1, 1024, kNmsSmem, s>>>(reinterpret_cast<const float4*>(boxes), n, thr, keep);
+  DPB_CHECK_LAUNCH("nms_sorted");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- merge
+__global__ void __launch_bounds__(1024) rpn_merge_kernel(RpnArgs a) {
+  extern __shared__ unsigned long long mkeys[];   // 8192
+  __shared__ unsigned s_n;
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) s_n = 0;
+  for (int i = threadIdx.x; i < 8192; i += blockDim.x) mkeys[i] = 0ull;
+  __syncthreads();
+  const int total = 5 * a.pre_topk;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int lvl = i / a.pre_topk, t = i - lvl * a.pre_topk;
+    const long long slot = ((long long)b * 5 + lvl) * a.pre_topk + t;
+    if (t < a.cand_count[b * 5 + lvl] && a.cand_keep[slot]) {
+      // key 0 is reserved for "empty": ordered keys of finite floats are never 0
+      mkeys[i] = ((unsigned long long)f2ord(a.cand_scores[slot]) << 32) | (0xFFFFFFFFu - (uint32_t)i);
+      atomicAdd(&s_n, 1u);
+    }
+  }
+  __syncthreads();
+  bitonic_sort_desc(mkeys, 8192);
+  const int n = (int)s_n < a.post_topk ? (int)s_n : a.post_topk;
+  for (int t = threadIdx.x; t < a.post_topk; t += blockDim.x) {
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sc = 0.f;
+    if (t < n) {
+      const uint32_t i = 0xFFFFFFFFu - (uint32_t)(mkeys[t] & 0xFFFFFFFFull);
+      const int lvl = i / a.pre_topk, tt = i - lvl * a.pre_topk;
+      const long long slot = ((long long)b * 5 + lvl) * a.pre_topk + tt;
+      bx = reinterpret_cast<const float4*>(a.cand_boxes)[slot];
+      sc = a.cand_scores[slot];
+    }
+    reinterpret_cast<float4*>(a.prop_boxes)[(long long)b * a.post_topk + t] = bx;
+    a.prop_scores[(long long)b * a.post_topk + t] = sc;
+  }
+  if (threadIdx.x == 0) a.prop_count[b] = n;
+}
+
+int launch_rpn_merge(const RpnArgs& a, cudaStream_t s) {
+  if (5 * a.pre_topk > 8192) { set_error("rpn_merge: too many candidates"); return -1; }
+  static bool once = false;
+  if (!once) { if (ensure_smem((const void*)rpn_merge_kernel, 8192 * 8)) return -3; once = true; }
+  rpn_merge_kernel<<<a.B, 1024, 8192 * 8, s>>>(a);
+  DPB_CHECK_LAUNCH("rpn_merge");
+  return 0;
+}
+
+}  // namespace dpb

@@ -1,0 +1,162 @@
+"""Python owner of a dpb200 model + sessions (device memory via torch, compute via libdpb200.so)."""
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+from .config import ModelSpec
+from .weights import Packed, pack_state_dict
+
+_DTYPES = {0: torch.bfloat16, 1: torch.float32, 2: torch.int32, 3: torch.uint8}
+
+
+class Session:
+    """Launch plan for one (batch, H0, W0, dtype) on one device."""
+
+    def __init__(self, engine: "Engine", batch: int, h0: int, w0: int, src_u8: bool):
+        self.engine, self.batch, self.h0, self.w0, self.src_u8 = engine, batch, h0, w0, src_u8
+        spec = engine.spec
+        nbytes = lib.dpb200_session_workspace_bytes(engine.handle, batch, h0, w0)
+        if nbytes == 0:
+            raise _lib.DPB200Error("session_workspace_bytes failed: " + _lib.last_error())
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=engine.device)
+        self.workspace.zero_()
+        h = C.c_void_p()
+        check(lib.dpb200_session_create(engine.handle, batch, h0, w0, int(src_u8), self.workspace.data_ptr(),
+                                        nbytes, C.byref(h)), "dpb200_session_create")
+        self.handle = h
+        n = batch * spec.dets_per_image
+        s = spec.out_size
+        dev = engine.device
+        self.pred_boxes = torch.zeros(batch, spec.dets_per_image, 4, device=dev)
+        self.scores = torch.zeros(batch, spec.dets_per_image, device=dev)
+        self.det_count = torch.zeros(batch, dtype=torch.int32, device=dev)
+        self.det_offsets = torch.zeros(batch + 1, dtype=torch.int32, device=dev)
+        self.coarse = torch.zeros(n, spec.coarse_ch, s, s, device=dev)
+        self.fine = torch.zeros(n, 25, s, s, device=dev)
+        self.u = torch.zeros(n, 25, s, s, device=dev)
+        self.v = torch.zeros(n, 25, s, s, device=dev)
+        self.io = _lib.ForwardIO()
+        self.io.pred_boxes = self.pred_boxes.data_ptr(); self.io.scores = self.scores.data_ptr()
+        self.io.det_count = self.det_count.data_ptr(); self.io.det_offsets = self.det_offsets.data_ptr()
+        self.io.coarse = self.coarse.data_ptr(); self.io.fine = self.fine.data_ptr()
+        self.io.u = self.u.data_ptr(); self.io.v = self.v.data_ptr()
+        g = (C.c_int32 * 4)()
+        lib.dpb200_session_geometry(self.handle, C.byref(g))
+        self.hr, self.wr, self.hp, self.wp = g[0], g[1], g[2], g[3]
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            lib.dpb200_session_destroy(h)
+            self.handle = None
+
+    @property
+    def launches(self) -> int:
+        return lib.dpb200_session_launch_count(self.handle)
+
+    def run(self, images: torch.Tensor, bgr: bool = True):
+        """images: [B,H0,W0,3] contiguous on the engine's device (fp32, or uint8 for a u8 session).
+        Enqueues the whole forward on the current stream; results land in the session's output tensors."""
+        assert images.is_cuda and images.is_contiguous() and tuple(images.shape) == (self.batch, self.h0, self.w0, 3)
+        assert images.dtype == (torch.uint8 if self.src_u8 else torch.float32)
+        self.io.images = images.data_ptr()
+        self.io.bgr = int(bgr)
+        check(lib.dpb200_session_run(self.handle, C.byref(self.io), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+              "dpb200_session_run")
+
+    def tap(self, name: str) -> torch.Tensor:
+        """View of an intermediate tensor inside the workspace (stage-parity tests)."""
+        p = C.c_void_p(); shape = (C.c_int64 * 4)(); dt = C.c_int32()
+        check(lib.dpb200_session_tap(self.handle, name.encode(), C.byref(p), C.byref(shape), C.byref(dt)), "tap")
+        dtype = _DTYPES[dt.value]
+        off = p.value - self.workspace.data_ptr()
+        numel = shape[0] * shape[1] * shape[2] * shape[3]
+        nb = numel * torch.empty(0, dtype=dtype).element_size()
+        return self.workspace[off:off + nb].view(dtype).view(shape[0], shape[1], shape[2], shape[3])
+
+    def results(self) -> List[Dict[str, torch.Tensor]]:
+        """Per-image result dicts in the reference's output format (synchronises)."""
+        spec = self.engine.spec
+        counts = self.det_count.cpu().tolist()
+        offs = self.det_offsets.cpu().tolist()
+        out = []
+        for b in range(self.batch):
+            d, o = counts[b], offs[b]
+            out.append({
+                "image_size": torch.tensor([self.h0, self.w0], dtype=torch.int64, device=self.engine.device),
+                "pred_boxes": self.pred_boxes[b, :d],
+                "scores": self.scores[b, :d],
+                "pred_classes": torch.zeros(d, dtype=torch.int64, device=self.engine.device),
+                "pred_densepose_coarse_segm": self.coarse[o:o + d],
+                "pred_densepose_fine_segm": self.fine[o:o + d],
+                "pred_densepose_u": self.u[o:o + d],
+                "pred_densepose_v": self.v[o:o + d],
+            })
+        return out
+
+
+class Engine:
+    """Packed weights + native model handle on one CUDA device."""
+
+    def __init__(self, spec: ModelSpec, state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 packed: Optional[Dict[str, Packed]] = None, device: Optional[torch.device] = None):
+        _lib.require_device()
+        self.spec = spec
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if packed is None:
+            if state_dict is None:
+                raise ValueError("Engine needs a state_dict or packed weights")
+            packed = pack_state_dict(state_dict, spec, self.device)
+        self.packed = packed
+        cfg = _lib.ModelConfig()
+        cfg.depth = spec.depth; cfg.head = 0 if spec.head == "v1convx" else 1
+        cfg.decoder_on = int(spec.decoder_on); cfg.pooler_res = spec.pooler_res; cfg.coarse_ch = spec.coarse_ch
+        cfg.score_thresh = spec.score_thresh; cfg.nms_test = spec.nms_test; cfg.rpn_nms = spec.rpn_nms
+        cfg.dets_per_image = spec.dets_per_image; cfg.rpn_pre_topk = spec.rpn_pre_topk
+        cfg.rpn_post_topk = spec.rpn_post_topk; cfg.min_size = spec.min_size; cfg.max_size = spec.max_size
+        for i in range(3):
+            cfg.pixel_mean[i] = spec.pixel_mean[i]; cfg.pixel_std[i] = spec.pixel_std[i]
+        cfg.input_rgb = int(spec.input_format == "RGB")
+        arr = (_lib.Weight * len(packed))()
+        self._names = []
+        for i, (name, (d0, d1, cin_pad, cout_pad)) in enumerate(packed.items()):
+            nb = name.encode()
+            self._names.append(nb)
+            arr[i].name = nb
+            arr[i].data0 = d0.data_ptr()
+            arr[i].data1 = d1.data_ptr() if d1 is not None else None
+            arr[i].cin_pad, arr[i].cout_pad = cin_pad, cout_pad
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.dpb200_model_create(C.byref(cfg), arr, len(packed), C.byref(h)), "dpb200_model_create")
+        self.handle = h
+        self._sessions: Dict[Tuple[int, int, int, bool], Session] = {}
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            self._sessions.clear()
+            lib.dpb200_model_destroy(h)
+            self.handle = None
+
+    def session(self, batch: int, h0: int, w0: int, src_u8: bool = False) -> Session:
+        key = (batch, h0, w0, src_u8)
+        s = self._sessions.get(key)
+        if s is None:
+            with torch.cuda.device(self.device):
+                s = Session(self, batch, h0, w0, src_u8)
+            self._sessions[key] = s
+        return s
+
+    def forward_batch(self, images: torch.Tensor, bgr: bool = True) -> List[Dict[str, torch.Tensor]]:
+        """images [B,H,W,3] (HWC, fp32 or uint8) on any device -> list of reference-format result dicts."""
+        images = images.to(self.device, non_blocking=True).contiguous()
+        if images.dtype not in (torch.uint8, torch.float32):
+            images = images.float()
+        s = self.session(images.shape[0], images.shape[1], images.shape[2], images.dtype == torch.uint8)
+        with torch.cuda.device(self.device):
+            s.run(images, bgr)
+        return s.results()

@@ -62,6 +62,152 @@ typedef struct dpb200_conv2d_args {
 
 int dpb200_conv2d(const dpb200_conv2d_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Stage ops (HBM-bound kernels).  Each replaces the reference seam named beside it.
+ */
+
+/* DefaultPredictor.forward resize (detectron2/engine/defaults.py:85-89, F.interpolate bilinear,
+ * scale_factor=k) fused with GeneralizedRCNN.preprocess_image (meta_arch/rcnn.py:156-181: normalise,
+ * zero-pad to /32).  src [B,H0,W0,3] HWC fp32 (or u8); dst = stem layout [B,Hp,Wx,4] bf16, image column x
+ * stored at x+3, Wx = Wp+16, everything outside the resized image is 0. */
+typedef struct dpb200_preprocess_args {
+  const void* src; int32_t src_u8; int32_t b, h0, w0;
+  int32_t hr, wr; float inv_scale; int32_t flip_rgb;
+  float mean[3]; float std[3];
+  void* dst; int32_t hp, wx;
+} dpb200_preprocess_args;
+int dpb200_preprocess(const dpb200_preprocess_args* a, void* stream);
+
+/* F.max_pool2d(k=3,s=2,p=1) of BasicStem.forward (backbone/resnet.py:353). NHWC bf16. */
+int dpb200_maxpool3x3s2(const void* x, void* y, int32_t b, int32_t h, int32_t w, int32_t c, void* stream);
+
+/* nn.Upsample(x2, bilinear, align_corners=False) of Decoder (densepose/modeling/roi_heads/roi_head.py:63). */
+int dpb200_upsample2x(const void* x, void* y, int32_t b, int32_t h, int32_t w, int32_t c, void* stream);
+/* Decoder.forward sum of the four scale heads (roi_head.py:71-77): out = a + up2(b3) + up2(b4) + up2(b5). */
+int dpb200_decoder_merge(const void* a, const void* b3, const void* b4, const void* b5, void* out,
+                         int32_t b, int32_t h, int32_t w, int32_t c, void* stream);
+
+/* RPN proposal selection: RPN.forward / _decode_proposals (proposal_generator/rpn.py:319-394),
+ * Box2BoxTransform.apply_deltas (box_regression.py:74-112), DefaultAnchorGenerator
+ * (anchor_generator.py:165-231) and find_top_rpn_proposals (proposal_utils.py:19-134) including the
+ * per-level batched_nms (layers/nms.py:9-20).  head[l]: [B,H_l,W_l,16] fp32 (3 logits, 12 deltas, pad). */
+typedef struct dpb200_rpn_args {
+  const float* head[5]; int32_t h[5], w[5]; float stride[5]; float anchors[5][12];
+  int32_t b, pre_topk, post_topk; float nms_thresh; float clip_x, clip_y;
+  float* cand_boxes; float* cand_scores; int32_t* cand_count; uint8_t* cand_keep;   /* workspace */
+  float* prop_boxes; float* prop_scores; int32_t* prop_count;                        /* outputs   */
+} dpb200_rpn_args;
+int dpb200_rpn_proposals(const dpb200_rpn_args* a, void* stream);
+
+/* torchvision.ops.nms on boxes already sorted by descending score (layers/nms.py:20). n <= 1024.
+ * keep[i] is 1 on entry for usable rows; on exit 1 for kept rows. */
+int dpb200_nms_sorted(const float* boxes, int32_t n, float thr, uint8_t* keep, void* stream);
+
+/* ROIPooler.forward (modeling/poolers.py:187-227) with assign_boxes_to_levels (poolers.py:15-51) and
+ * torchvision.ops.roi_align(aligned=False, sampling_ratio=2) (layers/roi_align.py:58-65).
+ * feat[l]: NHWC bf16 [B,H_l,W_l,C]; rois [R,5]; out [R,P,P,C] bf16 (fp32 if out_fp32). */
+typedef struct dpb200_roi_align_args {
+  const void* feat[4]; int32_t h[4], w[4]; float scale[4]; int32_t n_levels; int32_t c;
+  const float* rois; const int32_t* n_rois; int32_t r, p;
+  void* out; int32_t out_fp32;
+} dpb200_roi_align_args;
+int dpb200_roi_align(const dpb200_roi_align_args* a, void* stream);
+
+/* FastRCNNOutputLayers.inference (roi_heads/fast_rcnn.py:257-326) + fast_rcnn_inference_single_image
+ * (fast_rcnn.py:86-140) + detector_postprocess (modeling/postprocessing.py:11-61). */
+typedef struct dpb200_box_predict_args {
+  const float* head; const float* prop_boxes; const int32_t* prop_count; int32_t b, r;
+  float score_thresh, nms_thresh; int32_t topk; float scale_x, scale_y, out_w, out_h;
+  float* ws_boxes; uint8_t* ws_keep;
+  float* det_boxes_raw; float* det_boxes; float* det_scores; int32_t* det_count;
+} dpb200_box_predict_args;
+int dpb200_box_predict(const dpb200_box_predict_args* a, void* stream);
+
+/* nn.GroupNorm(32, C) + ReLU of DensePoseDeepLabHead (densepose/modeling/roi_heads/deeplab.py:45,70-73,90,101).
+ * x [R,HW,C] bf16 -> y [R,out_hw,y_cstride] bf16 (out_hw != hw only for hw == 1: broadcast, deeplab.py:109). */
+int dpb200_groupnorm_relu(const void* x, const float* gamma, const float* beta, void* y, int32_t r,
+                          int32_t hw, int32_t c, int32_t y_cstride, int32_t out_hw, const int32_t* n_valid,
+                          void* stream);
+/* nn.AdaptiveAvgPool2d(1) of ASPPPooling (deeplab.py:99). x [R,HW,C] bf16 -> y [R,C] bf16. */
+int dpb200_avgpool(const void* x, void* y, int32_t r, int32_t hw, int32_t c, const int32_t* n_valid, void* stream);
+
+/* interp2d (bilinear x2) of DensePoseChartPredictor.forward (densepose/modeling/predictors/chart.py:62-90).
+ * low [R,S,S,cpad] fp32 NHWC (coarse[kc], fine[25], u[25], v[25]) -> four NCHW fp32 [R,C,2S,2S]. */
+int dpb200_predictor_upsample(const float* low, int32_t r, int32_t s, int32_t cpad, int32_t kc,
+                              const int32_t* n_valid, float* coarse, float* fine, float* u, float* v,
+                              void* stream);
+
+/* DensePoseResultExtractor (visualizer.py:10-56): per-box resize + argmax + U/V gather.
+ * box_wh [D,2] = (max(int(w),1), max(int(h),1)); offsets [D+1] pixel prefix sums; labels int64 packed;
+ * uv fp32 packed (box i at 2*offsets[i]: U plane then V plane). */
+typedef struct dpb200_resample_args {
+  const float* coarse; const float* fine; const float* u; const float* v;
+  int32_t d, kc, s; const int32_t* box_wh; const int64_t* offsets;
+  int64_t* labels; float* uv; int64_t total_pixels;
+} dpb200_resample_args;
+int dpb200_dp_resample(const dpb200_resample_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole forward pass: DefaultPredictor.forward (engine/defaults.py:65-97) -> GeneralizedRCNN.inference
+ * (meta_arch/rcnn.py:110-154), batched over B independent images of one size.
+ */
+typedef struct dpb200_model_config {
+  int32_t depth;            /* 50 | 101  (MODEL.RESNETS.DEPTH)                                   */
+  int32_t head;             /* 0 DensePoseV1ConvXHead, 1 DensePoseDeepLabHead                     */
+  int32_t decoder_on;       /* ROI_DENSEPOSE_HEAD.DECODER_ON                                      */
+  int32_t pooler_res;       /* 14 | 28                                                            */
+  int32_t coarse_ch;        /* 15 | 2                                                             */
+  float score_thresh, nms_test, rpn_nms;
+  int32_t dets_per_image, rpn_pre_topk, rpn_post_topk;
+  int32_t min_size, max_size;
+  float pixel_mean[3], pixel_std[3];
+  int32_t input_rgb;        /* INPUT.FORMAT == "RGB"                                              */
+} dpb200_model_config;
+
+/* One packed parameter. conv / linear / deconv-phase: data0 = bf16 [cout_pad][k*cin_pad], data1 = fp32
+ * bias [cout_pad] (or NULL). GroupNorm: data0 = fp32 gamma, data1 = fp32 beta. Device pointers owned by
+ * the caller and kept alive for the model's lifetime. Names: see densepose_torchscript_b200/weights.py. */
+typedef struct dpb200_weight {
+  const char* name; const void* data0; const void* data1; int32_t cin_pad, cout_pad;
+} dpb200_weight;
+
+typedef struct dpb200_model dpb200_model;
+typedef struct dpb200_session dpb200_session;
+
+int dpb200_model_create(const dpb200_model_config* cfg, const dpb200_weight* w, int32_t n, dpb200_model** out);
+void dpb200_model_destroy(dpb200_model* m);
+
+/* A session fixes (batch, input height, input width, input dtype) and owns the launch plan (TMA
+ * descriptors, grid sizes) over a caller-provided workspace. */
+size_t dpb200_session_workspace_bytes(const dpb200_model* m, int32_t b, int32_t h0, int32_t w0);
+int dpb200_session_create(const dpb200_model* m, int32_t b, int32_t h0, int32_t w0, int32_t src_u8,
+                          void* workspace, size_t workspace_bytes, dpb200_session** out);
+void dpb200_session_destroy(dpb200_session* s);
+
+typedef struct dpb200_forward_io {
+  const void* images;       /* [B,H0,W0,3] HWC, fp32 or u8 as the session was created            */
+  int32_t bgr;              /* the reference's `bgr` argument (defaults.py:65)                    */
+  float* pred_boxes;        /* [B, dets_per_image, 4] original-image pixels                       */
+  float* scores;            /* [B, dets_per_image]                                                */
+  int32_t* det_count;       /* [B]                                                                */
+  int32_t* det_offsets;     /* [B+1] start of each image's rows in the packed DensePose tensors   */
+  float* coarse;            /* [B*dets_per_image, coarse_ch, 4S, 4S] packed, NCHW fp32            */
+  float* fine;              /* [B*dets_per_image, 25, 4S, 4S]                                     */
+  float* u;                 /* [B*dets_per_image, 25, 4S, 4S]                                     */
+  float* v;                 /* [B*dets_per_image, 25, 4S, 4S]                                     */
+} dpb200_forward_io;
+int dpb200_session_run(dpb200_session* s, const dpb200_forward_io* io, void* stream);
+
+/* Kernel launches one run enqueues, and their algorithmic FLOPs (2*MAC of every conv/linear at full
+ * detection capacity). */
+int dpb200_session_launch_count(const dpb200_session* s);
+double dpb200_session_flops(const dpb200_session* s);
+/* Resized / padded extents the session computes: out[0..3] = Hr, Wr, Hp, Wp. */
+void dpb200_session_geometry(const dpb200_session* s, int32_t out[4]);
+/* Intermediate tensors by name (stage-parity tests): device pointer, shape (up to 4 dims, NHWC), dtype
+ * (0 bf16, 1 fp32, 2 int32, 3 u8). Returns 0 if the name exists. */
+int dpb200_session_tap(const dpb200_session* s, const char* name, void** ptr, int64_t shape[4], int32_t* dtype);
+
 #ifdef __cplusplus
 }
 #endif

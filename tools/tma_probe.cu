@@ -58,7 +58,7 @@ static void run(const char* title, const CUtensorMap& tm, int mode, int c0, int 
                 int offw, int offh, int rows, int chans_to_print) {
   const int bytes = rows * 128;
   cudaMemset(d_out, 0, 256 * 128);
-  probe_kernel<<<1, 128, 48 * 1024>>>(tm, mode, c0, c1, c2, c3, offw, offh, bytes, d_out);
+  probe_kernel<<<1, 128, 40 * 1024>>>(tm, mode, c0, c1, c2, c3, offw, offh, bytes, d_out);
   cudaError_t e = cudaDeviceSynchronize();
   printf("== %s  coords(%d,%d,%d,%d) off(%d,%d): %s\n", title, c0, c1, c2, c3, offw, offh,
          cudaGetErrorString(e));
