@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Headline benchmark: DensePose R-CNN forward, images/sec at 800x1333 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+ours      : the B200 engine (libdpb200.so) on configs[1] = densepose_rcnn_R_50_FPN_s1x, bf16, batch 8 synthetic
+            800x1333 images per GPU (weak scaling: every rank runs its own batch, no collective on the data path).
+            value = whole-job images/s with inputs resident in HBM; e2e = same through Engine.forward with pinned
+            HOST inputs and HOST outputs (H2D + D2H inside the timed region).
+reference : the reference's CPU path (oracle port of the TorchScript model, fp32, all host threads), one
+            800x1333 image per step — rank 0 only.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "images/sec at 800x1333 (R50-FPN DensePose R-CNN forward)"
+CONFIG = "densepose_rcnn_R_50_FPN_s1x"
+
+
+# ------------------------------------------------------------------------------------------------ FLOP model
+def algorithmic_gflop(spec, hp: int, wp: int, rpn_props: int = 1000):
+    """(fixed GFLOP per image, GFLOP per detection): 2*MAC over conv / linear / deconv with the REAL channel
+    counts (579.7 + 28.73*D for R50 s1x at 800x1344)."""
+    def conv(h, w, cin, cout, k=1):
+        return 2.0 * h * w * cin * cout * k * k
+
+    f = conv(hp // 2, wp // 2, 3, 64, 7)
+    h, w, cin = hp // 4, wp // 4, 64
+    lv = []
+    for si, nb in enumerate(spec.blocks):
+        bott, cout = 64 << si, 256 << si
+        if si > 0:
+            h, w = h // 2, w // 2
+        for bi in range(nb):
+            if bi == 0:
+                f += conv(h, w, cin, cout)
+            f += conv(h, w, cin, bott) + conv(h, w, bott, bott, 3) + conv(h, w, bott, cout)
+            cin = cout
+        lv.append((h, w, cout))
+    for (h, w, c) in lv:
+        f += conv(h, w, c, 256) + conv(h, w, 256, 256, 3)
+    rpn = [(h, w) for (h, w, _) in lv] + [((lv[3][0] + 1) // 2, (lv[3][1] + 1) // 2)]
+    for (h, w) in rpn:
+        f += conv(h, w, 256, 256, 3) + conv(h, w, 256, 15)
+    f += rpn_props * 2.0 * (12544 * 1024 + 1024 * 1024 + 1024 * 6)
+    if spec.decoder_on:
+        (h2, w2, _), (h3, w3, _), (h4, w4, _), (h5, w5, _) = lv
+        n33 = h2 * w2 + h3 * w3 + (h4 * w4 + h3 * w3) + (h5 * w5 + h4 * w4 + h3 * w3)
+        f += 2.0 * n33 * 256 * 256 * 9 + conv(h2, w2, 256, 256)
+    s = spec.pooler_res
+    if spec.head == "v1convx":
+        d = conv(s, s, 256, 512, 3) + 7 * conv(s, s, 512, 512, 3)
+    else:
+        d = conv(s, s, 256, 256) + 3 * conv(s, s, 256, 256, 3) + conv(1, 1, 256, 256) + conv(s, s, 1280, 256)
+        d += conv(s, s, 256, 512, 3) + 7 * conv(s, s, 512, 512, 3)
+    d += 2.0 * (2 * s) * (2 * s) * 512 * (spec.coarse_ch + 75) * 4      # ConvTranspose 4x4/2: 4 taps per output pixel
+    return f / 1e9, d / 1e9
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples if len(s) >= 7 for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1388.0), d.get("hbm_gbs", 6548.2), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_rate(height, width, steps, warmup, config=CONFIG, max_seconds=120.0):
+    """images/s of the reference's CPU path (oracle port, fp32, mode='ref') on this host."""
+    from oracle import densepose_oracle as O
+    from oracle import weights as W
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = O.SPECS[config]
+    sd = W.make_state_dict(spec, 0)
+    img = W.synthetic_image(height, width, seed=1)
+    small = W.synthetic_image(64, 96, seed=2)
+    O.forward(small, sd, spec, mode="ref")              # thread-pool / allocator warm-up on a tiny image
+    budget = time.perf_counter() + max_seconds
+    for _ in range(min(warmup, 1)):                      # one full-size warm-up at most: each forward is seconds
+        O.forward(img, sd, spec, mode="ref")
+    t0 = time.perf_counter()
+    dets, done = 0, 0
+    for _ in range(steps):
+        dets = len(O.forward(img, sd, spec, mode="ref")["scores"])
+        done += 1
+        if time.perf_counter() > budget:                 # bounded sample: keep the whole arm within minutes
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, dt / done, torch.get_num_threads(), dets, done
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(a.steps, 1), a.warmup
+    rate, sec, threads, dets, steps = cpu_reference_rate(a.height, a.width, steps, warmup)
+    sample = f"{steps} step(s) x 1 synthetic {a.height}x{a.width} image, {dets} detections, fp32 oracle port of the reference"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": a.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{CONFIG} fp32, one synthetic {a.height}x{a.width} image per step, seeded random weights, CPU"},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(a):
+    import torch.distributed as dist
+    from densepose_torchscript_b200 import synth
+    from densepose_torchscript_b200.config import BUILTIN
+    from densepose_torchscript_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    spec = BUILTIN[a.config]
+    B, H, W = a.batch, a.height, a.width
+
+    eng = Engine(spec, synth.make_state_dict(spec, 0), device=dev)
+    host = torch.stack([synth.synthetic_image(H, W, seed=100 + rank * B + i) for i in range(B)]).contiguous().pin_memory()
+    images = host.to(dev)
+    sess = eng.session(B, H, W, False)
+    fixed, per_det = algorithmic_gflop(spec, sess.hp, sess.wp, spec.rpn_post_topk)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        sess.run(images)
+    barrier()
+    counts = sess.det_count.cpu()
+    dets = int(counts.sum())
+
+    # ---- value: inputs resident in HBM
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        sess.run(images)
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: pinned host images in, reference-format outputs back to pinned host memory, every step
+    outs_dev = [sess.pred_boxes, sess.scores, sess.det_count, sess.det_offsets, sess.coarse, sess.fine, sess.u, sess.v]
+    outs_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs_dev]
+    h2d = host.numel() * host.element_size()
+    d2h = sum(t.numel() * t.element_size() for t in outs_dev)
+
+    def e2e_step():
+        images.copy_(host, non_blocking=True)
+        sess.run(images)
+        for hbuf, dbuf in zip(outs_host, outs_dev):
+            hbuf.copy_(dbuf, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(a.steps):
+        e2e_step()
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    # ---- per-launch profile (CUDA events on the launch stream) for the roofline of the dominant kernel
+    info = sess.op_info()
+    prof = None
+    for _ in range(3):
+        p = sess.profile(images)
+        prof = p if prof is None else [x + y for x, y in zip(prof, p)]
+    prof = [x / 3 for x in prof]
+    conv_ms = sum(ms for (n, _), ms in zip(info, prof) if n.startswith("conv:"))
+    total_ms = sum(prof)
+
+    # max over ranks
+    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    d = torch.tensor([dets], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(d, op=dist.ReduceOp.SUM)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    total_dets = float(d[0])
+
+    if rank == 0:
+        peak_tf, peak_hbm, which = measured_peaks()
+        n_img = world * B * a.steps
+        gflop_step = B * fixed + per_det * dets                 # this rank's algorithmic work per step
+        achieved = gflop_step / conv_ms                          # GFLOP / ms = TFLOP/s, conv launches only
+        top = sorted(zip(prof, [n for n, _ in info]), reverse=True)[:5]
+        line = {
+            "metric": METRIC, "value": n_img / (ms_dev / 1e3), "unit": "images/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{a.config} bf16 (fp32 accumulate), batch {B} synthetic {H}x{W} images per GPU, "
+                                   f"seeded calibrated random weights, {total_dets / world / B:.0f} detections/image",
+                       "batch_per_gpu": B, "image": [H, W], "padded": [sess.hp, sess.wp], "parallelism": f"shard{world}",
+                       "l2": f"per-step working set {sess.workspace.numel() / 1e9:.1f} GB >> 126 MB L2 (no flush needed)"},
+            "e2e": {"value": n_img / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / a.steps,
+                    "note": "pinned host fp32 images in; boxes, scores, counts and all four DensePose tensors (full "
+                            "capacity) copied to pinned host memory every step"},
+            "gpu_launches": sess.launches * a.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "traffic": None, "kernel": "conv_igemm_kernel", "peak_source": which + " bf16_tflops_sustained",
+                         "launches_per_step": sum(1 for n, _ in info if n.startswith("conv:")),
+                         "kernel_ms_per_step": conv_ms, "kernel_share_of_step": conv_ms / total_ms,
+                         "algorithmic_gflop_per_step": gflop_step,
+                         "step_tflops": gflop_step / (ms_dev / a.steps)},
+            "top_launches_ms": [[round(ms, 4), n] for ms, n in top],
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            rate, sec, threads, cdets, _ = cpu_reference_rate(H, W, 1, 0, a.config)
+            line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                                    "sample": f"1 synthetic {H}x{W} image ({cdets} detections), fp32 oracle port of the "
+                                              f"reference forward, {sec:.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=CONFIG)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--height", type=int, default=800)
+    ap.add_argument("--width", type=int, default=1333)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        if "--steps" not in " ".join(sys.argv):
+            a.steps = 2
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

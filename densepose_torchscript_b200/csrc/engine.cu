@@ -42,6 +42,8 @@ struct dpb200_session {
   char* ws = nullptr; size_t ws_bytes = 0, ws_used = 0;
   bool dry = false;     // dry run: only measure the workspace
   std::vector<std::function<int(cudaStream_t)>> ops;
+  std::vector<std::string> op_names;     // "conv:<weight name>" or the stage kernel's name
+  std::vector<double> op_flops;          // padded-shape 2*MAC at full capacity (conv ops), else 0
   std::vector<ConvPlan*> plans;
   std::map<std::string, TensorInfo> taps;
   double flops = 0;
@@ -134,7 +136,10 @@ struct Builder {
                    : (void*)(reinterpret_cast<bf16*>(y.p) + o.out_off);
     d.n_valid = o.n_valid;
     if (d.cout_pad > y.C && !o.out_sx) { fail = -12; set_error("conv %s: output has %d channels, weights %d", wname.c_str(), y.C, d.cout_pad); return; }
-    s->flops += 2.0 * x.N * d.H_out * d.W_out * (double)w->cout_pad * d.kh * d.kw * w->cin_pad;
+    const double fl = 2.0 * x.N * d.H_out * d.W_out * (double)w->cout_pad * d.kh * d.kw * w->cin_pad;
+    s->flops += fl;
+    s->op_names.push_back("conv:" + wname);
+    s->op_flops.push_back(fl);
     if (s->dry) { s->ops.push_back([](cudaStream_t) { return 0; }); return; }
     ConvPlan* plan = new ConvPlan();
     int r = conv_plan_build(plan, d, m->num_sms);
@@ -142,8 +147,10 @@ struct Builder {
     s->plans.push_back(plan);
     s->ops.push_back([plan](cudaStream_t st) { return conv_plan_launch(*plan, st); });
   }
-  void op(std::function<int(cudaStream_t)> f) {
+  void op(std::function<int(cudaStream_t)> f, const char* name = "stage") {
     if (fail) return;
+    s->op_names.push_back(name);
+    s->op_flops.push_back(0.0);
     if (s->dry) { s->ops.push_back([](cudaStream_t) { return 0; }); return; }
     s->ops.push_back(std::move(f));
   }
@@ -192,7 +199,7 @@ int build_plan(dpb200_session* s) {
       p.src = ss->io->images;
       p.flip_rgb = (ss->m->cfg.input_rgb && ss->io->bgr) ? 1 : 0;   // defaults.py:82-83
       return launch_preprocess(p, st);
-    });
+    }, "preprocess");
   }
   // ---- a3 stem: 7x7/2 conv as 7 row taps over a 16-pixel (64-element) sliding window
   T4 stem = b.act(B, Hp / 2, Wp / 2, 64);
@@ -206,7 +213,7 @@ int build_plan(dpb200_session* s) {
   T4 pool = b.act(B, Hp / 4, Wp / 4, 64);
   b.op([=](cudaStream_t st) {
     return launch_maxpool3x3s2((const bf16*)stem.p, (bf16*)pool.p, B, stem.H, stem.W, 64, st);
-  });
+  }, "maxpool3x3s2");
   b.tap("stem_pool", pool);
 
   // ---- a4 res2..res5
@@ -297,19 +304,19 @@ int build_plan(dpb200_session* s) {
   b.tap_raw("rpn_cand_boxes", ra.cand_boxes, B, 5, K, 4, 1);
   b.tap_raw("rpn_cand_scores", ra.cand_scores, B, 5, K, 1, 1);
   b.tap_raw("rpn_cand_keep", ra.cand_keep, B, 5, K, 1, 3);
-  b.op([ra](cudaStream_t st) { return launch_rpn_topk_decode(ra, st); });
-  b.op([ra](cudaStream_t st) { return launch_rpn_nms(ra, st); });
-  b.op([ra](cudaStream_t st) { return launch_rpn_merge(ra, st); });
+  b.op([ra](cudaStream_t st) { return launch_rpn_topk_decode(ra, st); }, "rpn_topk_decode");
+  b.op([ra](cudaStream_t st) { return launch_rpn_nms(ra, st); }, "rpn_nms");
+  b.op([ra](cudaStream_t st) { return launch_rpn_merge(ra, st); }, "rpn_merge");
 
   // ---- a11-a13 box branch
   float* rois_box = (float*)b.alloc((size_t)B * R * 5 * 4);
-  b.op([=](cudaStream_t st) { return launch_proposal_rois(ra.prop_boxes, ra.prop_count, B, R, rois_box, st); });
+  b.op([=](cudaStream_t st) { return launch_proposal_rois(ra.prop_boxes, ra.prop_count, B, R, rois_box, st); }, "proposal_rois");
   T4 box_pooled = b.act(B * R, 7, 7, 256);
   {
     RoiAlignArgs a{};
     for (int l = 0; l < 4; ++l) { a.feat[l] = (const bf16*)pf[l].p; a.H[l] = pf[l].H; a.W[l] = pf[l].W; a.scale[l] = 1.0f / (float)(4 << l); }
     a.n_levels = 4; a.C = 256; a.rois = rois_box; a.n_rois = nullptr; a.R = B * R; a.P = 7; a.out = box_pooled.p; a.out_fp32 = 0;
-    b.op([a](cudaStream_t st) { return launch_roi_align(a, st); });
+    b.op([a](cudaStream_t st) { return launch_roi_align(a, st); }, "roi_align_box");
   }
   b.tap("box_pooled", box_pooled);
   T4 fc_in = box_pooled; fc_in.H = 1; fc_in.W = 1; fc_in.C = 7 * 7 * 256;
@@ -335,7 +342,7 @@ int build_plan(dpb200_session* s) {
       BoxPredictArgs a = ss->bp;
       a.det_boxes = ss->io->pred_boxes; a.det_scores = ss->io->scores; a.det_count = ss->io->det_count;
       return launch_box_predict(a, st);
-    });
+    }, "box_predict");
   }
   const int Rd = B * topk;
   s->rois_dp = (float*)b.alloc((size_t)Rd * 5 * 4);
@@ -345,7 +352,7 @@ int build_plan(dpb200_session* s) {
     b.op([ss, B, topk](cudaStream_t st) {
       return launch_pack_rois(ss->bp.det_boxes_raw, ss->io->det_count, B, topk, ss->rois_dp, ss->dp_total,
                               ss->io->det_offsets, st);
-    });
+    }, "pack_rois");
   }
   b.tap_raw("dp_total", s->dp_total, 1, 1, 1, 1, 2);
   const int* nv = s->dp_total;
@@ -364,7 +371,7 @@ int build_plan(dpb200_session* s) {
         b.conv("roi_heads.decoder.p" + std::to_string(l + 2) + "." + std::to_string(2 * kk), x, y, o);
         if (kk != l - 1) {
           T4 up = b.act(B, y.H * 2, y.W * 2, 256);
-          b.op([=](cudaStream_t st) { return launch_upsample2x((const bf16*)y.p, (bf16*)up.p, B, y.H, y.W, 256, st); });
+          b.op([=](cudaStream_t st) { return launch_upsample2x((const bf16*)y.p, (bf16*)up.p, B, y.H, y.W, 256, st); }, "upsample2x");
           x = up;
         } else {
           x = y;   // the last upsample is fused into the merge
@@ -376,7 +383,7 @@ int build_plan(dpb200_session* s) {
     b.op([=](cudaStream_t st) {
       return launch_decoder_merge((const bf16*)d2.p, (const bf16*)branch[0].p, (const bf16*)branch[1].p,
                                   (const bf16*)branch[2].p, (bf16*)merged.p, B, merged.H, merged.W, 256, st);
-    });
+    }, "decoder_merge");
     T4 dec = b.act(B, pf[0].H, pf[0].W, 256);
     { Builder::ConvOpt o; o.k = 1; b.conv("roi_heads.decoder.predictor", merged, dec, o); }
     b.tap("decoder", dec);
@@ -391,7 +398,7 @@ int build_plan(dpb200_session* s) {
     RoiAlignArgs a{};
     for (int l = 0; l < dp_levels; ++l) { a.feat[l] = (const bf16*)dp_feat[l].p; a.H[l] = dp_feat[l].H; a.W[l] = dp_feat[l].W; a.scale[l] = 1.0f / (float)(4 << l); }
     a.n_levels = dp_levels; a.C = 256; a.rois = s->rois_dp; a.n_rois = nv; a.R = Rd; a.P = P; a.out = dp_pooled.p;
-    b.op([a](cudaStream_t st) { return launch_roi_align(a, st); });
+    b.op([a](cudaStream_t st) { return launch_roi_align(a, st); }, "roi_align_dp");
   }
   b.tap("dp_pooled", dp_pooled);
   // ---- a16/a17 head
@@ -416,7 +423,7 @@ int build_plan(dpb200_session* s) {
       if (!w) return;
       const float* g = (const float*)w->d0; const float* be = (const float*)w->d1;
       const bf16* xp = (const bf16*)x.p; const int C = x.C; const int R_ = Rd;
-      b.op([=](cudaStream_t st) { return launch_groupnorm_relu(xp, g, be, y, R_, hw_in, C, ycs, hw_out, nv, st); });
+      b.op([=](cudaStream_t st) { return launch_groupnorm_relu(xp, g, be, y, R_, hw_in, C, ycs, hw_out, nv, st); }, "groupnorm_relu");
     };
     // ASPP branches (deeplab.py:112-144); branch 3 (rate 56 >= P) only ever sees its centre tap
     const int dil[3] = {1, 6, 12};
@@ -429,7 +436,7 @@ int build_plan(dpb200_session* s) {
       b.conv(hp + "ASPP.convs.3.0", dp_pooled, tmp256, o);
       gn(hp + "ASPP.convs.3.1", tmp256, (bf16*)cat.p + 768, 1280, HW, HW); }
     T4 pooled = b.act(Rd, 1, 1, 256), pooled_c = b.act(Rd, 1, 1, 256);
-    b.op([=](cudaStream_t st) { return launch_avgpool((const bf16*)dp_pooled.p, (bf16*)pooled.p, Rd, HW, 256, nv, st); });
+    b.op([=](cudaStream_t st) { return launch_avgpool((const bf16*)dp_pooled.p, (bf16*)pooled.p, Rd, HW, 256, nv, st); }, "avgpool");
     { Builder::ConvOpt o; o.k = 1; o.n_valid = nv; o.no_bias = true; b.conv(hp + "ASPP.convs.4.1", pooled, pooled_c, o); }
     gn(hp + "ASPP.convs.4.2", pooled_c, (bf16*)cat.p + 1024, 1280, 1, HW);
     T4 proj = b.act(Rd, P, P, 256);
@@ -465,7 +472,7 @@ int build_plan(dpb200_session* s) {
     b.op([ss, Rd, Kc, nv](cudaStream_t st) {
       return launch_predictor_upsample(ss->low, Rd, ss->low_S, ss->low_C, Kc, nv, ss->io->coarse, ss->io->fine,
                                        ss->io->u, ss->io->v, st);
-    });
+    }, "predictor_upsample");
   }
   return b.fail;
 }
@@ -523,6 +530,34 @@ int dpb200_session_run(dpb200_session* s, const dpb200_forward_io* io, void* str
 }
 
 int dpb200_session_launch_count(const dpb200_session* s) { return s ? (int)s->ops.size() : 0; }
+
+int dpb200_session_op_info(const dpb200_session* s, int32_t i, char* name, int32_t cap, double* flops) {
+  if (!s || i < 0 || i >= (int)s->ops.size()) { set_error("op_info: bad index"); return -1; }
+  if (name && cap > 0) { strncpy(name, s->op_names[i].c_str(), cap - 1); name[cap - 1] = 0; }
+  if (flops) *flops = s->op_flops[i];
+  return 0;
+}
+
+int dpb200_session_profile(dpb200_session* s, const dpb200_forward_io* io, void* stream, float* ms, int32_t cap) {
+  if (!s || !io || !ms) { set_error("session_profile: null argument"); return -1; }
+  const int n = (int)s->ops.size();
+  if (cap < n) { set_error("session_profile: need room for %d ops", n); return -1; }
+  s->io = io;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) cudaEventCreate(&e);
+  cudaEventRecord(ev[0], st);
+  int rc = 0;
+  for (int i = 0; i < n && !rc; ++i) {
+    rc = s->ops[i](st);
+    cudaEventRecord(ev[i + 1], st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (!rc && e != cudaSuccess) { set_error("session_profile: %s", cudaGetErrorString(e)); rc = -5; }
+  if (!rc) for (int i = 0; i < n; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+  for (auto& e2 : ev) cudaEventDestroy(e2);
+  return rc;
+}
 double dpb200_session_flops(const dpb200_session* s) { return s ? s->flops : 0.0; }
 void dpb200_session_geometry(const dpb200_session* s, int32_t out[4]) {
   out[0] = s->Hr; out[1] = s->Wr; out[2] = s->Hp; out[3] = s->Wp;

@@ -67,6 +67,25 @@ class Session:
         check(lib.dpb200_session_run(self.handle, C.byref(self.io), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
               "dpb200_session_run")
 
+    def op_info(self) -> List[Tuple[str, float]]:
+        out = []
+        buf = C.create_string_buffer(160)
+        fl = C.c_double()
+        for i in range(self.launches):
+            check(lib.dpb200_session_op_info(self.handle, i, buf, 160, C.byref(fl)), "op_info")
+            out.append((buf.value.decode(), fl.value))
+        return out
+
+    def profile(self, images: torch.Tensor, bgr: bool = True) -> List[float]:
+        """One run with CUDA events around every launch (on the current stream); returns ms per launch."""
+        self.io.images = images.data_ptr()
+        self.io.bgr = int(bgr)
+        n = self.launches
+        ms = (C.c_float * n)()
+        check(lib.dpb200_session_profile(self.handle, C.byref(self.io),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream), ms, n), "session_profile")
+        return list(ms)
+
     def tap(self, name: str) -> torch.Tensor:
         """View of an intermediate tensor inside the workspace (stage-parity tests)."""
         p = C.c_void_p(); shape = (C.c_int64 * 4)(); dt = C.c_int32()

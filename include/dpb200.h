@@ -201,6 +201,11 @@ int dpb200_session_run(dpb200_session* s, const dpb200_forward_io* io, void* str
 /* Kernel launches one run enqueues, and their algorithmic FLOPs (2*MAC of every conv/linear at full
  * detection capacity). */
 int dpb200_session_launch_count(const dpb200_session* s);
+/* Name ("conv:<weight>" or the stage kernel) and padded-shape 2*MAC of launch i. */
+int dpb200_session_op_info(const dpb200_session* s, int32_t i, char* name, int32_t cap, double* flops);
+/* Like dpb200_session_run but brackets every launch with CUDA events on `stream`, synchronises, and writes
+ * the per-launch milliseconds to ms[0..launch_count). Measurement aid for bench.py, not the serving path. */
+int dpb200_session_profile(dpb200_session* s, const dpb200_forward_io* io, void* stream, float* ms, int32_t cap);
 double dpb200_session_flops(const dpb200_session* s);
 /* Resized / padded extents the session computes: out[0..3] = Hr, Wr, Hp, Wp. */
 void dpb200_session_geometry(const dpb200_session* s, int32_t out[4]);

@@ -1,0 +1,359 @@
+"""Stage-isolated parity: every CUDA kernel, called through the C-ABI, against the CPU oracle on identical
+(seeded) inputs.  Integer / index / ordering results must be bit-exact; floating-point tolerances are
+written beside each check.  Run on a B200:  python -m pytest tests -m gpu -x -q
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _util import bf16, frac_equal, nchw, nhwc_bf16_cuda, rel_l2
+from oracle import densepose_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from densepose_torchscript_b200 import ops as _ops
+    from densepose_torchscript_b200 import _lib
+    _lib.require_device()
+    return _ops
+
+
+# ----------------------------------------------------------------------------------------------- conv
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad, dil, relu, res(0 none,1 same,2 up2)
+    (1, 16, 16, 64, 64, 1, 1, 0, 1, False, 0),
+    (2, 13, 21, 128, 48, 3, 1, 1, 1, False, 0),
+    (1, 50, 84, 256, 256, 3, 1, 1, 1, True, 0),
+    (2, 25, 42, 128, 512, 1, 1, 0, 1, True, 1),
+    (2, 50, 84, 256, 128, 1, 2, 0, 1, False, 0),
+    (1, 50, 84, 512, 256, 1, 1, 0, 1, False, 2),
+    (300, 1, 1, 1024, 1024, 1, 1, 0, 1, True, 0),
+    (3, 28, 28, 256, 256, 3, 1, 6, 6, False, 0),
+    (3, 28, 28, 256, 256, 3, 1, 12, 12, False, 0),
+    (7, 14, 14, 256, 512, 3, 1, 1, 1, True, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("tiled", [False, True])
+def test_conv_igemm_matches_oracle(ops, case, tiled):
+    N, H, W, Cin, Cout, k, stride, pad, dil, relu, res_mode = case
+    g = torch.Generator().manual_seed(hash(case) % 100000)
+    x = bf16(torch.randn(N, Cin, H, W, generator=g))
+    w = bf16(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k))
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x, w, b, stride=stride, padding=pad, dilation=dil)        # wrappers.py:105-107 on the same bf16 operands
+    res = None
+    if res_mode == 1:
+        res = bf16(torch.randn_like(ref))
+        ref = ref + res
+    elif res_mode == 2:
+        res = bf16(torch.randn(N, Cout, (ref.shape[2] + 1) // 2, (ref.shape[3] + 1) // 2, generator=g))
+        ref = ref + F.interpolate(res, scale_factor=2.0, mode="nearest")[:, :, :ref.shape[2], :ref.shape[3]]   # fpn.py:152-154
+    if relu:
+        ref = F.relu(ref)
+    packed, bias, _, cout_pad = ops.pack_conv_weight(w.cuda(), b.cuda())
+    out = ops.conv2d(nhwc_bf16_cuda(x), packed, bias, k, k, stride=stride, pad=pad, dil=dil, relu=relu,
+                     res=None if res is None else nhwc_bf16_cuda(res), res_shift=1 if res_mode == 2 else 0,
+                     tiled=tiled)
+    torch.cuda.synchronize()
+    got = nchw(out[..., :Cout])
+    # bf16 output: half an ulp of the largest magnitude (2^-9 relative) plus fp32 accumulation-order noise
+    tol = float(ref.abs().max()) * 2.0 ** -8 + 1e-3
+    assert float((got - ref).abs().max()) <= tol
+    assert rel_l2(got, bf16(ref)) < 3e-3
+
+
+def test_conv_fp32_out_and_n_valid(ops):
+    g = torch.Generator().manual_seed(5)
+    x = bf16(torch.randn(9, 256, 28, 28, generator=g))
+    w = bf16(torch.randn(6, 256, 1, 1, generator=g) / 16)
+    b = torch.randn(6, generator=g)
+    packed, bias, _, cout_pad = ops.pack_conv_weight(w.cuda(), b.cuda())
+    out = torch.full((9, 28, 28, cout_pad), -7.0, device="cuda")
+    nv = torch.tensor([5], dtype=torch.int32, device="cuda")
+    ops.conv2d(nhwc_bf16_cuda(x), packed, bias, 1, 1, out_fp32=True, n_valid=nv, out=out)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x, w, b)
+    assert float((nchw(out[:5, ..., :6]) - ref[:5]).abs().max()) < 2e-4      # fp32 accumulate, fp32 store
+    assert bool((out[5:] == -7.0).all())                                      # images >= n_valid untouched
+    assert bool((out[:5, ..., 6:] == 0).all())                                # padded output channels are zero
+
+
+# ----------------------------------------------------------------------------------------------- preprocess
+@pytest.mark.parametrize("h0,w0", [(240, 600), (300, 200), (97, 131)])
+def test_preprocess_matches_oracle(ops, h0, w0):
+    spec = O.SPECS["densepose_rcnn_R_50_FPN_s1x"]
+    g = torch.Generator().manual_seed(h0)
+    img = torch.rand(h0, w0, 3, generator=g) * 255.0
+    image, _, _ = O.predictor_resize(img, spec)
+    ref, padding = O.preprocess_image(image, spec, O.Numerics("bf16"))          # [1,3,Hp,Wp]
+    k = O.resize_scale(h0, w0, spec)
+    dst, (hr, wr, hp, wp) = ops.preprocess(img[None].cuda().contiguous(), k, spec.pixel_mean, spec.pixel_std)
+    torch.cuda.synchronize()
+    assert (hr, wr) == tuple(image.shape[1:]) and (hp, wp) == tuple(ref.shape[2:])
+    got = dst[0, :, 3:3 + wp, :3].permute(2, 0, 1).float().cpu()
+    assert frac_equal(got, ref[0]) > 0.995          # identical up to rare 1-ulp bf16 flips (FMA vs mul+add on the host)
+    assert float((got - ref[0]).abs().max()) <= 1.0   # one bf16 ulp at |x| in [128, 256)
+    assert bool((dst[0, :, :3] == 0).all()) and bool((dst[0, :, 3 + wp:] == 0).all()) and bool((dst[..., 3] == 0).all())
+    assert bool((dst[0, hr:] == 0).all()) and bool((dst[0, :, 3 + wr:] == 0).all())   # zero padding in normalised space
+
+
+def test_maxpool_exact(ops):
+    g = torch.Generator().manual_seed(1)
+    x = bf16(torch.randn(2, 64, 38, 50, generator=g)).relu()
+    ref = F.max_pool2d(x, 3, 2, 1)                                              # resnet.py:353
+    got = nchw(ops.maxpool3x3s2(nhwc_bf16_cuda(x)))
+    assert torch.equal(got, ref)
+
+
+def test_upsample_and_decoder_merge(ops):
+    g = torch.Generator().manual_seed(2)
+    x = bf16(torch.randn(2, 256, 13, 21, generator=g))
+    ref = bf16(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False))   # roi_head.py:63
+    got = nchw(ops.upsample2x(nhwc_bf16_cuda(x)))
+    assert frac_equal(got, ref) > 0.99 and rel_l2(got, ref) < 2e-3
+    a = bf16(torch.randn(2, 256, 26, 42, generator=g))
+    bs = [bf16(torch.randn(2, 256, 13, 21, generator=g)) for _ in range(3)]
+    ref = a
+    for t in bs:
+        ref = ref + F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=False)   # roi_head.py:73-77
+    ref = bf16(ref)
+    got = nchw(ops.decoder_merge(nhwc_bf16_cuda(a), *[nhwc_bf16_cuda(t) for t in bs]))
+    assert frac_equal(got, ref) > 0.98 and rel_l2(got, ref) < 3e-3
+
+
+# ----------------------------------------------------------------------------------------------- RPN
+def _rpn_inputs(seed, sizes, quant=None):
+    g = torch.Generator().manual_seed(seed)
+    logits, deltas, heads = [], [], []
+    for (h, w) in sizes:
+        lg = torch.randn(1, 3, h, w, generator=g) * 2.0
+        if quant:
+            lg = torch.round(lg / quant) * quant
+        dl = torch.randn(1, 12, h, w, generator=g) * 0.5
+        dl[:, 2::4] += 1.0
+        dl[:, 3::4] += 1.0
+        logits.append(lg); deltas.append(dl)
+        head = torch.zeros(1, h, w, 16)
+        head[..., :3] = lg.permute(0, 2, 3, 1)
+        head[..., 3:15] = dl.permute(0, 2, 3, 1)
+        heads.append(head.cuda().contiguous())
+    return logits, deltas, heads
+
+
+def test_rpn_proposals_match_oracle(ops):
+    spec = O.SPECS["densepose_rcnn_R_50_FPN_s1x"]
+    sizes = [(64, 96), (32, 48), (16, 24), (8, 12), (4, 6)]            # a 256x384 padded image
+    Hp, Wp = 256, 384
+    logits, deltas, heads = _rpn_inputs(11, sizes)
+    lg, dl = O.rpn_flatten(logits, deltas)
+    anchors = O.grid_anchors(sizes)
+    props = [O.apply_deltas(d.reshape(-1, 4), a, (1.0, 1.0, 1.0, 1.0)).view(1, -1, 4) for a, d in zip(anchors, dl)]
+    ref = O.find_top_rpn_proposals(props, lg, (Wp, Hp), spec)
+    boxes, scores, counts, dbg = ops.rpn_proposals(heads, clip_x=float(Hp), clip_y=float(Wp))
+    torch.cuda.synchronize()
+    # per-level top-k: selected scores are bit-exact and in descending order; decoded+clipped boxes within fp32 exp() ulps
+    for l, (p, s) in enumerate(zip(props, lg)):
+        k = min(1000, s.shape[1])
+        ts, ti = s[0].topk(k)
+        assert int(dbg["cand_count"][0, l]) == k
+        assert torch.equal(dbg["cand_scores"][0, l, :k].cpu(), ts)
+        ref_boxes = O.clip_boxes(p[0, ti], (Wp, Hp))                    # quirk 1: swapped extents
+        assert torch.allclose(dbg["cand_boxes"][0, l, :k].cpu(), ref_boxes, rtol=1e-5, atol=1e-3)
+    n = int(counts[0])
+    assert n == len(ref["proposal_boxes"])
+    assert torch.equal(scores[0, :n].cpu(), ref["objectness_logits"])   # NMS keep set + merged order: exact
+    assert torch.allclose(boxes[0, :n].cpu(), ref["proposal_boxes"], rtol=1e-5, atol=1e-3)
+    assert float(boxes[0, :n, 0::2].max()) <= Hp and float(boxes[0, :n, 1::2].max()) <= Wp
+
+
+def test_rpn_topk_with_many_ties(ops):
+    sizes = [(40, 64), (20, 32), (10, 16), (5, 8), (3, 4)]
+    logits, deltas, heads = _rpn_inputs(12, sizes, quant=0.5)           # heavy duplication of logit values
+    lg, _ = O.rpn_flatten(logits, deltas)
+    _, _, _, dbg = ops.rpn_proposals(heads, clip_x=160.0, clip_y=256.0)
+    torch.cuda.synchronize()
+    for l, s in enumerate(lg):
+        k = min(1000, s.shape[1])
+        ts, _ = s[0].topk(k)
+        assert torch.equal(dbg["cand_scores"][0, l, :k].cpu(), ts)      # the multiset of selected scores is exact
+
+
+# ----------------------------------------------------------------------------------------------- NMS
+@pytest.mark.parametrize("n,thr,seed", [(1, 0.5, 0), (33, 0.5, 1), (1000, 0.7, 2), (1000, 0.5, 3), (777, 0.3, 4)])
+def test_nms_keep_order_bitexact(ops, n, thr, seed):
+    g = torch.Generator().manual_seed(seed)
+    xy = torch.rand(n, 2, generator=g) * 300
+    wh = torch.rand(n, 2, generator=g) * 120
+    boxes = torch.cat([xy, xy + wh], 1)
+    if n > 10:
+        boxes[3] = boxes[2]                        # duplicates
+        boxes[5, 2:] = boxes[5, :2]                # zero-area box: 0/0 = NaN never suppresses
+        boxes[7] = boxes[5]
+    scores = torch.rand(n, generator=g)
+    order = torch.sort(scores, descending=True, stable=True)[1]
+    sb = boxes[order]
+    ref_keep = O.nms(sb, scores[order], thr)       # indices into the sorted list, ascending
+    got = ops.nms_sorted(sb.cuda(), thr).cpu()
+    assert torch.equal(torch.nonzero(got).squeeze(1), ref_keep)
+
+
+# ----------------------------------------------------------------------------------------------- ROIAlign
+def test_roi_align_multilevel_bitexact(ops):
+    g = torch.Generator().manual_seed(21)
+    shapes = [(50, 84), (25, 42), (13, 21), (7, 11)]
+    feats = [bf16(torch.randn(2, 256, h, w, generator=g)) for h, w in shapes]
+    n = 64
+    xy = torch.rand(n, 2, generator=g) * torch.tensor([300.0, 180.0])
+    wh = torch.exp(torch.rand(n, 2, generator=g) * 5.0 + 1.0)           # ~3 .. 400 px: all four levels
+    boxes = torch.cat([xy, xy + wh], 1)
+    boxes[0] = torch.tensor([-40.0, -20.0, 30.0, 25.0])
+    boxes[1] = torch.tensor([10.0, 10.0, 10.0, 10.0])
+    boxes[2] = torch.tensor([320.0, 190.0, 900.0, 700.0])
+    bidx = (torch.arange(n) % 2).float()
+    rois = torch.cat([bidx[:, None], boxes], 1)
+    levels = O.assign_boxes_to_levels(boxes)
+    assert len(torch.unique(levels)) == 4
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    ref = torch.zeros(n, 256, 7, 7)
+    for i in range(n):
+        l = int(levels[i])
+        b = int(bidx[i])
+        r = torch.cat([torch.zeros(1, 1), boxes[i:i + 1]], 1)
+        ref[i] = O.roi_align(feats[l][b:b + 1], r, 7, scales[l])[0]
+    fe = [nhwc_bf16_cuda(f) for f in feats]
+    got32 = ops.roi_align(fe, rois.cuda(), 7, scales, out_fp32=True)
+    got16 = ops.roi_align(fe, rois.cuda(), 7, scales, out_fp32=False)
+    torch.cuda.synchronize()
+    g32 = got32.permute(0, 3, 1, 2).cpu()
+    # identical sampling indices and weights: fp32 results equal to the last bit or two (sum order is the same)
+    assert float((g32 - ref).abs().max()) <= 2e-6
+    assert frac_equal(g32, ref) > 0.95
+    assert frac_equal(got16.permute(0, 3, 1, 2).float().cpu(), bf16(ref)) > 0.999
+
+
+def test_roi_align_single_level_28(ops):
+    g = torch.Generator().manual_seed(22)
+    feat = bf16(torch.randn(1, 256, 60, 84, generator=g))
+    n = 9
+    xy = torch.rand(n, 2, generator=g) * torch.tensor([250.0, 150.0])
+    wh = torch.rand(n, 2, generator=g) * 150 + 2
+    rois = torch.cat([torch.zeros(n, 1), xy, xy + wh], 1)
+    ref = O.roi_align(feat, rois, 28, 0.25)
+    nv = torch.tensor([7], dtype=torch.int32, device="cuda")
+    got = ops.roi_align([nhwc_bf16_cuda(feat)], rois.cuda(), 28, [0.25], out_fp32=True, n_rois=nv)
+    torch.cuda.synchronize()
+    g32 = got.permute(0, 3, 1, 2).cpu()
+    assert float((g32[:7] - ref[:7]).abs().max()) <= 2e-6
+    assert bool((g32[7:] == 0).all())              # rows past the device-side count are not touched
+
+
+# ----------------------------------------------------------------------------------------------- box head tail
+def test_box_predict_matches_oracle(ops):
+    spec = O.SPECS["densepose_rcnn_R_50_FPN_s1x"]
+    g = torch.Generator().manual_seed(31)
+    R, n_prop = 1000, 940
+    xy = torch.rand(R, 2, generator=g) * torch.tensor([1000.0, 600.0])
+    wh = torch.rand(R, 2, generator=g) * 300 + 4
+    props = torch.cat([xy, xy + wh], 1)
+    cls = torch.randn(R, 2, generator=g) * 1.5
+    dl = torch.randn(R, 4, generator=g) * 0.5
+    head = torch.zeros(R, 16)
+    head[:, :2], head[:, 2:6] = cls, dl
+    boxes = O.apply_deltas(dl[:n_prop], props[:n_prop], (10.0, 10.0, 5.0, 5.0))
+    probs = F.softmax(cls[:n_prop], dim=-1)
+    det = O.fast_rcnn_inference_single_image(boxes, probs, torch.tensor([1344, 800]), spec)
+    H0, W0, Hr, Wr = 480, 800, 800, 1333
+    for k in ("pred_densepose_coarse_segm", "pred_densepose_fine_segm", "pred_densepose_u", "pred_densepose_v"):
+        det[k] = torch.zeros(len(det["scores"]), 1)
+    post = O.detector_postprocess(det, H0, W0, (0, 1344 - Wr, 0, 800 - Hr))
+    raw, out_boxes, scores, count = ops.box_predict(
+        head.cuda(), props[None].cuda().contiguous(), torch.tensor([n_prop], dtype=torch.int32, device="cuda"),
+        spec.score_thresh, spec.nms_test, spec.dets_per_image, W0 / Wr, H0 / Hr, float(W0), float(H0))
+    torch.cuda.synchronize()
+    d = int(count[0])
+    assert d == len(det["scores"])
+    assert torch.allclose(scores[0, :d].cpu(), det["scores"], rtol=0, atol=2e-6)      # softmax: expf ulps
+    assert torch.allclose(raw[0, :d].cpu(), det["pred_boxes"], rtol=1e-5, atol=2e-3)  # unclipped (quirk 2)
+    assert torch.allclose(out_boxes[0, :d].cpu(), post["pred_boxes"], rtol=1e-5, atol=2e-3)
+    assert float(out_boxes[0, :d, 0::2].max()) <= W0 and float(out_boxes[0, :d, 1::2].max()) <= H0
+
+
+def test_box_predict_no_detections(ops):
+    head = torch.zeros(1000, 16)
+    head[:, 1] = 10.0                                                   # background wins everywhere
+    props = torch.rand(1, 1000, 4) * 100
+    props[..., 2:] += props[..., :2]
+    raw, boxes, scores, count = ops.box_predict(head.cuda(), props.cuda().contiguous(),
+                                                torch.tensor([1000], dtype=torch.int32, device="cuda"),
+                                                0.3, 0.5, 100, 1.0, 1.0, 800.0, 600.0)
+    torch.cuda.synchronize()
+    assert int(count[0]) == 0
+
+
+# ----------------------------------------------------------------------------------------------- DeepLab pieces
+@pytest.mark.parametrize("C", [256, 512])
+def test_groupnorm_relu(ops, C):
+    g = torch.Generator().manual_seed(C)
+    x = bf16(torch.randn(5, C, 28, 28, generator=g) * 2 + 0.3)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    ref = bf16(F.relu(F.group_norm(x, 32, gamma, beta, eps=1e-5)))       # deeplab.py:45,70-73
+    xin = x.permute(0, 2, 3, 1).reshape(5, 784, C).contiguous().to(torch.bfloat16).cuda()
+    got = ops.groupnorm_relu(xin, gamma.cuda(), beta.cuda()).float().cpu().view(5, 28, 28, C).permute(0, 3, 1, 2)
+    assert rel_l2(got, ref) < 3e-3 and frac_equal(got, ref) > 0.97
+
+
+def test_avgpool_and_broadcast_gn(ops):
+    g = torch.Generator().manual_seed(41)
+    x = bf16(torch.randn(4, 256, 28, 28, generator=g))
+    xin = x.permute(0, 2, 3, 1).reshape(4, 784, 256).contiguous().to(torch.bfloat16).cuda()
+    pooled = ops.avgpool(xin)
+    ref = bf16(F.adaptive_avg_pool2d(x, 1)[:, :, 0, 0])                   # deeplab.py:99
+    assert rel_l2(pooled.float().cpu(), ref) < 3e-3
+    gamma, beta = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.2
+    got = ops.groupnorm_relu(pooled.view(4, 1, 256), gamma.cuda(), beta.cuda(), out_hw=784)
+    refb = bf16(F.relu(F.group_norm(pooled.float().cpu().view(4, 256, 1, 1), 32, gamma, beta, eps=1e-5)))
+    refb = refb.expand(4, 256, 28, 28)                                   # bilinear from 1x1 == broadcast (deeplab.py:109)
+    assert rel_l2(got.float().cpu().view(4, 28, 28, 256).permute(0, 3, 1, 2), refb) < 3e-3
+
+
+# ----------------------------------------------------------------------------------------------- predictor tail + extractor
+@pytest.mark.parametrize("S,kc", [(56, 2), (28, 15)])
+def test_predictor_upsample(ops, S, kc):
+    g = torch.Generator().manual_seed(S)
+    C = kc + 75
+    cpad = (C + 15) // 16 * 16
+    low = torch.randn(3, C, S, S, generator=g)
+    ref = F.interpolate(low, scale_factor=2.0, mode="bilinear", align_corners=False)   # chart.py:72-74
+    lin = torch.zeros(3, S, S, cpad)
+    lin[..., :C] = low.permute(0, 2, 3, 1)
+    outs = ops.predictor_upsample(lin.cuda().contiguous(), kc)
+    torch.cuda.synchronize()
+    got = torch.cat([o.cpu() for o in outs], dim=1)
+    assert float((got - ref).abs().max()) < 2e-6
+
+
+def test_dp_resample_matches_extractor(ops):
+    g = torch.Generator().manual_seed(51)
+    D, S = 6, 112
+    low = [torch.randn(D, c, 14, 14, generator=g) for c in (2, 25, 25, 25)]
+    coarse, fine, u, v = [F.interpolate(t, size=(S, S), mode="bicubic", align_corners=False) for t in low]
+    boxes = torch.tensor([[10.2, 20.7, 150.9, 300.1], [0.0, 0.0, 0.4, 0.3], [5.5, 5.5, 260.0, 90.2],
+                          [100.0, 50.0, 131.9, 400.0], [7.0, 9.0, 119.0, 121.0], [3.3, 4.4, 60.6, 30.1]])
+    inst = {"pred_boxes": boxes, "pred_densepose_coarse_segm": coarse, "pred_densepose_fine_segm": fine,
+            "pred_densepose_u": u, "pred_densepose_v": v}
+    ref, ref_xywh = O.extract_results(inst)                                # visualizer.py:46-56
+    got, xywh = ops.dp_resample(coarse.cuda(), fine.cuda(), u.cuda(), v.cuda(), boxes.cuda())
+    torch.cuda.synchronize()
+    assert torch.allclose(xywh.cpu(), ref_xywh)
+    for r, q in zip(ref, got):
+        assert r["labels"].shape == q["labels"].shape and q["labels"].dtype == torch.int64
+        agree = (r["labels"] == q["labels"].cpu()).float().mean()
+        assert agree >= 0.999                                              # argmax flips only on fp32 near-ties
+        same = r["labels"] == q["labels"].cpu()
+        assert float((r["uv"] - q["uv"].cpu())[:, same].abs().max()) < 1e-5
