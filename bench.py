@@ -72,36 +72,56 @@ def algorithmic_gflop(spec, hp: int, wp: int, rpn_props: int = 1000):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """Samples SM clock, power and throttle reasons through NVML every 100 ms while the timed region runs."""
+
     def __init__(self, index: int):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self._stop, self._thread, self.err = index, [], False, None, None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
             return
-        threading.Thread(target=self._read, daemon=True).start()
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append([x.strip() for x in line.split(",")])
+    def _loop(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append((sm, mx, pw, rs))
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                return
+            time.sleep(0.1)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
-        mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples if len(s) >= 7 for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self._stop = True
+        if self._thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
+        self._thread.join(timeout=2)
+        nv = self.nv
+        sm = sorted(s[0] for s in self.samples)
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted({n for s in self.samples for n, bit in names.items() if s[3] & bit})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((s[1] for s in self.samples), default=None),
+                "power_w_max": max((s[2] for s in self.samples), default=None), "reasons": reasons, "samples": len(sm)}
 
 
 def measured_peaks():
@@ -234,6 +254,10 @@ def run_ours(a):
         p = sess.profile(images)
         prof = p if prof is None else [x + y for x, y in zip(prof, p)]
     prof = [x / 3 for x in prof]
+    if a.profile_out and rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(a.profile_out)), exist_ok=True)
+        with open(a.profile_out, "w") as f:
+            json.dump([{"i": i, "name": n, "ms": ms, "padded_gflop": fl / 1e9} for i, ((n, fl), ms) in enumerate(zip(info, prof))], f, indent=0)
     conv_ms = sum(ms for (n, _), ms in zip(info, prof) if n.startswith("conv:"))
     total_ms = sum(prof)
 
@@ -295,6 +319,7 @@ def main():
     ap.add_argument("--height", type=int, default=800)
     ap.add_argument("--width", type=int, default=1333)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default="", help="write the per-launch ms profile (JSON) here")
     a = ap.parse_args()
     if a.impl == "reference":
         if "--steps" not in " ".join(sys.argv):

@@ -93,7 +93,7 @@ def spec_from_yaml(path: str, min_score: float = 0.3, nms_thresh: float = None) 
         depth=int(model.get("RESNETS", {}).get("DEPTH", 50)),
         head=heads[head_name],
         decoder_on=bool(dp.get("DECODER_ON", True)),
-        pooler_res=int(dp.get("POOLER_RESOLUTION", 14)),
+        pooler_res=int(dp.get("POOLER_RESOLUTION", 28)),          # densepose/config.py:177
         coarse_ch=int(dp.get("NUM_COARSE_SEGM_CHANNELS", 2)),
         score_thresh=float(min_score),
         nms_test=float(model.get("ROI_HEADS", {}).get("NMS_THRESH_TEST", 0.5)),

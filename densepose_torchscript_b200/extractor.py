@@ -1,0 +1,60 @@
+"""Device-side replacement for the reference's per-box result extraction (visualizer.py:10-56).
+
+`DensePoseResultExtractor()(instances)` returns the same structure as the reference — a list with one
+{'labels': int64 [h, w], 'uv': float32 [2, h, w]} per detection, plus boxes_xywh — but the bilinear resize,
+the 25-way argmax and the U/V gather run in one CUDA kernel over all boxes instead of a Python loop of
+F.interpolate / boolean-mask scatters (46-74 ms per box on the CPU).
+"""
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+
+
+def extract_boxes_xywh_from_instances(instances: Dict[str, torch.Tensor]) -> torch.Tensor:
+    boxes_xywh = instances["pred_boxes"].clone()        # visualizer.py:40-43
+    boxes_xywh[:, 2:] -= boxes_xywh[:, :2]
+    return boxes_xywh
+
+
+class DensePoseResultExtractor:
+    def __call__(self, instances: Dict[str, torch.Tensor]) -> Tuple[List[Dict[str, torch.Tensor]], Optional[torch.Tensor]]:
+        boxes = instances["pred_boxes"]
+        if not boxes.is_cuda:
+            raise RuntimeError("DensePoseResultExtractor (dpb200) runs on the GPU; got CPU tensors")
+        results, boxes_xywh = ops.dp_resample(
+            instances["pred_densepose_coarse_segm"].float(), instances["pred_densepose_fine_segm"].float(),
+            instances["pred_densepose_u"].float(), instances["pred_densepose_v"].float(), boxes.float())
+        return results, boxes_xywh
+
+
+class End2EndVisualizer:
+    """visualizer.py:132-139: blends the part-label map (I channel) over the image with a JET colormap."""
+
+    def __init__(self, alpha: float = 0.7, inplace: bool = True):
+        self.extractor = DensePoseResultExtractor()
+        self.alpha = alpha
+        self.inplace = inplace
+
+    def visualize(self, image_bgr: Any, outputs: Dict[str, torch.Tensor]):
+        import cv2
+        import numpy as np
+
+        img = image_bgr if self.inplace else image_bgr.copy()
+        results, boxes_xywh = self.extractor(outputs)
+        boxes = boxes_xywh.long().cpu().tolist()
+        for res, (x, y, w, h) in zip(results, boxes):
+            labels = res["labels"].to(torch.uint8).cpu().numpy()
+            h_, w_ = labels.shape
+            x0, y0 = max(x, 0), max(y, 0)
+            x1, y1 = min(x + w_, img.shape[1]), min(y + h_, img.shape[0])
+            if x1 <= x0 or y1 <= y0:
+                continue
+            sub = labels[y0 - y:y1 - y, x0 - x:x1 - x]
+            color = cv2.applyColorMap((sub.astype(np.float32) * (255.0 / 24.0)).astype(np.uint8), cv2.COLORMAP_JET)
+            mask = (sub > 0)[..., None]
+            roi = img[y0:y1, x0:x1]
+            blended = (roi.astype(np.float32) * (1 - self.alpha) + color.astype(np.float32) * self.alpha).astype(np.uint8)
+            img[y0:y1, x0:x1] = np.where(mask, blended, roi)
+        return img

@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""Drop-in for the reference's export.py (export.py:12-41): config + weights -> a TorchScript file.
+
+    python export.py <cfg.yaml | builtin config name> <weights | ""> [--min_score 0.3] [--nms_thresh T] [--fp16]
+
+writes exported/<cfgstem>_fp{32,16}.pt holding the scripted DensePoseB200Predictor (the packed weights and
+one custom op, torch.ops.dpb200.forward).  Weights: a torch state_dict (.pth / .pt, optionally under a
+"model" key) or a detectron2-format .pkl ({"model": {name: ndarray}, "__author__": ...}); an empty string
+uses the seeded synthetic weights (no network here to fetch the model zoo).
+"""
+import argparse
+import os
+import pickle
+
+import torch
+
+from densepose_torchscript_b200 import synth
+from densepose_torchscript_b200.config import BUILTIN, spec_from_yaml
+from densepose_torchscript_b200.predictor import DensePoseB200Predictor
+
+
+def load_weights(path: str):
+    """detectron2/checkpoint/detection_checkpoint.py:49-90, minus the network handlers and the Caffe2 renames."""
+    if path.endswith(".pkl"):
+        with open(path, "rb") as f:
+            data = pickle.load(f, encoding="latin1")
+        if "model" in data and "__author__" in data:
+            return {k: torch.as_tensor(v) for k, v in data["model"].items()}
+        raise ValueError("Caffe2-format .pkl checkpoints need the detectron2 name conversion (not implemented yet); "
+                         "convert to a detectron2-format .pkl or a state_dict first")
+    data = torch.load(path, map_location="cpu", weights_only=False)
+    if isinstance(data, dict) and "model" in data and isinstance(data["model"], dict):
+        data = data["model"]
+    return data
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("cfg", type=str, help="Path to the config file (or a builtin config name)")
+    parser.add_argument("weights", type=str, help="Path to the weights file ('' = seeded synthetic weights)")
+    parser.add_argument("--min_score", default=0.3, type=float, help="Minimum score threshold (default: %(default)s)")
+    parser.add_argument("--nms_thresh", metavar="<threshold>", default=None, type=float, help="NMS threshold")
+    parser.add_argument("--fp16", action="store_true", help="Emit fp16 scores / DensePose tensors (like .half())")
+    args = parser.parse_args()
+
+    if os.path.exists(args.cfg):
+        spec = spec_from_yaml(args.cfg, min_score=args.min_score, nms_thresh=args.nms_thresh)
+    else:
+        from dataclasses import replace
+        spec = replace(BUILTIN[args.cfg], score_thresh=args.min_score)
+        if args.nms_thresh is not None:
+            spec = replace(spec, nms_test=args.nms_thresh)
+    sd = load_weights(args.weights) if args.weights else synth.make_state_dict(spec, 0)
+    predictor = DensePoseB200Predictor(spec, sd).eval()
+    predictor = torch.jit.script(predictor)
+    if args.fp16:
+        predictor = predictor.half()
+    os.makedirs("./exported", exist_ok=True)
+    stem = os.path.splitext(os.path.basename(args.cfg))[0]
+    save_path = os.path.join("./exported", stem + ("_fp16.pt" if args.fp16 else "_fp32.pt"))
+    torch.jit.save(predictor, save_path)
+    print(f"Model saved to {save_path}")
+
+
+if __name__ == "__main__":
+    main()

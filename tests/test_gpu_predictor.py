@@ -1,0 +1,68 @@
+"""The drop-in boundary on a real GPU: scripted predictor -> torch.ops.dpb200.forward -> C-ABI, and the
+device-side result extractor, against the engine / oracle."""
+import io
+
+import pytest
+import torch
+
+from oracle import densepose_oracle as O
+from oracle import weights as W
+
+pytestmark = pytest.mark.gpu
+NAME = "densepose_rcnn_R_50_FPN_s1x_legacy"
+
+
+@pytest.fixture(scope="module")
+def scripted():
+    from densepose_torchscript_b200.config import BUILTIN
+    from densepose_torchscript_b200.predictor import DensePoseB200Predictor
+    sd = W.make_state_dict(O.SPECS[NAME], 0)
+    pred = DensePoseB200Predictor(BUILTIN[NAME], W.add_aliases(sd, O.SPECS[NAME])).eval()
+    buf = io.BytesIO()
+    torch.jit.save(torch.jit.script(pred), buf)          # export.py:35-40
+    buf.seek(0)
+    return torch.jit.load(buf).eval().cuda(), sd         # run.py:18-26
+
+
+def test_scripted_predictor_matches_engine_and_reference_contract(scripted):
+    from densepose_torchscript_b200.config import BUILTIN
+    from densepose_torchscript_b200.engine import Engine
+    model, sd = scripted
+    img = W.synthetic_image(200, 320, seed=11)
+    out = model(img)                                       # CPU HWC float image, like run.py feeds it
+    eng = Engine(BUILTIN[NAME], sd)
+    ref = eng.forward_batch(img[None])[0]
+    assert set(out) == {"image_size", "pred_boxes", "scores", "pred_classes", "pred_densepose_coarse_segm",
+                        "pred_densepose_fine_segm", "pred_densepose_u", "pred_densepose_v"}
+    for k in out:
+        assert torch.equal(out[k], ref[k]), k
+    d = len(out["scores"])
+    assert out["pred_boxes"].dtype == torch.float32 and out["pred_classes"].dtype == torch.int64
+    assert out["image_size"].tolist() == [200, 320] and out["image_size"].dtype == torch.int64
+    assert out["pred_densepose_coarse_segm"].shape == (d, 15, 56, 56) and out["pred_densepose_u"].shape == (d, 25, 56, 56)
+    assert all(v.is_contiguous() for v in out.values())
+    out_chw = model(img.permute(2, 0, 1).contiguous())     # CHW input path (defaults.py:76-80)
+    assert torch.equal(out_chw["pred_boxes"], out["pred_boxes"])
+    with pytest.raises(Exception):
+        model(torch.zeros(4, 32, 32))
+    half = model.half()                                    # run.py:26
+    oh = half(img)
+    assert oh["scores"].dtype == torch.float16 and oh["pred_densepose_v"].dtype == torch.float16
+    assert oh["pred_boxes"].dtype == torch.float32        # boxes stay fp32 (box_regression.py:84)
+    model.float()
+
+
+def test_extractor_matches_reference_visualizer_semantics(scripted):
+    from densepose_torchscript_b200.extractor import DensePoseResultExtractor
+    model, _ = scripted
+    out = model(W.synthetic_image(200, 320, seed=12))
+    results, xywh = DensePoseResultExtractor()(out)
+    ref, ref_xywh = O.extract_results({k: v.float().cpu() for k, v in out.items()})     # visualizer.py:46-56
+    assert torch.allclose(xywh.cpu(), ref_xywh) and len(results) == len(ref)
+    agree, total = 0, 0
+    for r, q in zip(ref, results):
+        assert r["labels"].shape == q["labels"].shape and q["uv"].shape == r["uv"].shape
+        same = r["labels"] == q["labels"].cpu()
+        agree += int(same.sum()); total += same.numel()
+        assert float((r["uv"] - q["uv"].cpu())[:, same].abs().max()) < 1e-4
+    assert agree / max(total, 1) > 0.999                   # part-label pixel agreement vs the CPU extractor

@@ -1,0 +1,212 @@
+"""CPU-side checks: the C-ABI library loads and exports everything include/dpb200.h declares, the config
+reader, the weight packer's re-layouts, the scriptable predictor, and frame sharding over gloo (world 2)."""
+import io
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import REFERENCE, ROOT, have_reference
+
+
+# ------------------------------------------------------------------------------------------- C ABI
+def test_library_exports_every_declared_symbol():
+    from densepose_torchscript_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "dpb200.h")).read()
+    declared = set(re.findall(r"\b(dpb200_[a-z0-9_]+)\s*\(", header))
+    declared -= {"dpb200_pack_conv_weight"}                 # mentioned in a comment only
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(_lib.lib, name), f"{name} is declared in dpb200.h but not exported by libdpb200.so"
+    assert declared == set(_lib.EXPORTS)
+    assert _lib.lib.dpb200_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(rf"\bT {name}\b", out), name
+
+
+def test_no_device_means_loud_failure():
+    from densepose_torchscript_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert _lib.lib.dpb200_device_ok() == 0
+    with pytest.raises(_lib.DPB200Error):
+        _lib.require_device()
+    from densepose_torchscript_b200 import ops
+    with pytest.raises(_lib.DPB200Error):
+        ops.conv2d(torch.zeros(1, 4, 4, 64, dtype=torch.bfloat16), torch.zeros(16, 64, dtype=torch.bfloat16), None, 1, 1)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "densepose_torchscript_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+    for fn in ("export.py", "run.py"):
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", open(os.path.join(ROOT, fn)).read(), re.M), fn
+
+
+# ------------------------------------------------------------------------------------------- config
+def test_builtin_specs_match_oracle_specs():
+    from densepose_torchscript_b200.config import BUILTIN
+    from oracle import densepose_oracle as O
+    assert set(BUILTIN) == set(O.SPECS)
+    for k, s in BUILTIN.items():
+        o = O.SPECS[k]
+        for f in ("depth", "head", "decoder_on", "pooler_res", "coarse_ch", "score_thresh", "nms_test", "dets_per_image",
+                  "min_size", "max_size", "rpn_pre_topk", "rpn_post_topk", "rpn_nms", "pixel_mean", "pixel_std", "input_format"):
+            assert getattr(s, f) == getattr(o, f), (k, f)
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference yaml files not present")
+def test_yaml_reader_on_reference_configs():
+    from densepose_torchscript_b200.config import BUILTIN, spec_from_yaml
+    for name, spec in BUILTIN.items():
+        y = spec_from_yaml(os.path.join(REFERENCE, "configs", name + ".yaml"))
+        assert y == spec, name
+    wc = spec_from_yaml(os.path.join(REFERENCE, "configs", "densepose_rcnn_R_50_FPN_WC1_s1x.yaml"), min_score=0.5, nms_thresh=0.4)
+    assert (wc.head, wc.decoder_on, wc.pooler_res, wc.score_thresh, wc.nms_test) == ("v1convx", True, 28, 0.5, 0.4)
+
+
+# ------------------------------------------------------------------------------------------- weight packer
+def _unpack(packed, kh, kw, cin, cout):
+    w = packed[0].float().view(packed[3], kh, kw, packed[2])[:cout, :, :, :cin]
+    return w.permute(0, 3, 1, 2)
+
+
+def test_pack_folds_frozen_bn_and_accepts_aliases():
+    from densepose_torchscript_b200 import synth
+    from densepose_torchscript_b200.config import BUILTIN
+    from densepose_torchscript_b200.weights import canonicalize, pack_state_dict
+    spec = BUILTIN["densepose_rcnn_R_50_FPN_s1x"]
+    sd = synth.make_state_dict(spec, 0)
+    full = synth.add_aliases(sd, spec)
+    only_alias = {k: v for k, v in full.items() if not (".res2." in k or "fpn_lateral" in k or "decoder.p3" in k or "body_conv_fcn" in k)}
+    assert set(canonicalize(only_alias)) == set(sd)          # every duplicated registration maps back (quirk 10)
+    packed = pack_state_dict(only_alias, spec, "cpu")
+    p = "backbone.bottom_up.res3.1.conv2"
+    scale = sd[p + ".norm.weight"] * (sd[p + ".norm.running_var"] + 1e-5).rsqrt()
+    w_ref = (sd[p + ".weight"] * scale.view(-1, 1, 1, 1)).to(torch.bfloat16).float()
+    b_ref = sd[p + ".norm.bias"] - sd[p + ".norm.running_mean"] * scale
+    assert torch.equal(_unpack(packed[p], 3, 3, 128, 128), w_ref)
+    assert torch.allclose(packed[p][1][:128], b_ref)
+    # folded conv == conv + FrozenBN (batch_norm.py:54-62)
+    x = torch.randn(1, 128, 9, 11)
+    y_ref = F.batch_norm(F.conv2d(x, sd[p + ".weight"], padding=1), sd[p + ".norm.running_mean"], sd[p + ".norm.running_var"],
+                         sd[p + ".norm.weight"], sd[p + ".norm.bias"], training=False, eps=1e-5)
+    y = F.conv2d(x, sd[p + ".weight"] * scale.view(-1, 1, 1, 1), b_ref, padding=1)
+    assert torch.allclose(y, y_ref, atol=1e-4)
+
+
+def test_pack_special_layouts_are_exact_relayouts():
+    from densepose_torchscript_b200 import synth
+    from densepose_torchscript_b200.config import BUILTIN
+    from densepose_torchscript_b200.weights import pack_state_dict
+    spec = BUILTIN["densepose_rcnn_R_50_FPN_s1x"]
+    sd = synth.make_state_dict(spec, 0)
+    packed = pack_state_dict(sd, spec, "cpu")
+    g = torch.Generator().manual_seed(0)
+    # FC1: NHWC-flattened pooled features x permuted weight == reference flatten (c,y,x) x original weight
+    pooled = torch.randn(3, 256, 7, 7, generator=g)
+    w1 = packed["roi_heads.box_head.fc1"][0].float()
+    ref = F.linear(pooled.flatten(1), sd["roi_heads.box_head.fc1.weight"].to(torch.bfloat16).float())
+    got = F.linear(pooled.permute(0, 2, 3, 1).flatten(1), w1)
+    assert torch.allclose(got, ref, atol=1e-3)
+    # RPN head fusion: rows 0-2 objectness, 3-14 deltas, 15 zero
+    rp = packed["proposal_generator.rpn_head.pred"]
+    assert rp[3] == 16 and torch.equal(rp[0][15].float(), torch.zeros(256))
+    assert torch.equal(rp[0][:3].float(), sd["proposal_generator.rpn_head.objectness_logits.weight"].view(3, 256).to(torch.bfloat16).float())
+    # deconv phases: four 2x2 convs interleaved == ConvTranspose2d(k=4, s=2, p=1) (chart.py:45-59)
+    x = torch.randn(2, 512, 6, 6, generator=g)
+    names = ("ann_index_lowres", "index_uv_lowres", "u_lowres", "v_lowres")
+    wt = torch.cat([sd[f"roi_heads.densepose_predictor.{n}.weight"] for n in names], 1).to(torch.bfloat16).float()
+    bt = torch.cat([sd[f"roi_heads.densepose_predictor.{n}.bias"] for n in names], 0)
+    ref = F.conv_transpose2d(x, wt, bt, stride=2, padding=1)
+    out = torch.zeros_like(ref)
+    for py in range(2):
+        for px in range(2):
+            pk = packed[f"roi_heads.densepose_predictor.phase{py * 2 + px}"]
+            w = _unpack(pk, 2, 2, 512, 77)
+            xp = F.pad(x, (1 if px == 0 else 0, 0 if px == 0 else 1, 1 if py == 0 else 0, 0 if py == 0 else 1))
+            out[:, :, py::2, px::2] = F.conv2d(xp, w, pk[1][:77])
+    assert torch.allclose(out, ref, atol=1e-3)
+    # stem: 7 row taps x 16-pixel window == 7x7 stride-2 conv
+    st = packed["backbone.bottom_up.stem.conv1"]
+    w7 = st[0].float().view(64, 7, 16, 4)[:, :, :7, :3].permute(0, 3, 1, 2)
+    assert bool((st[0].float().view(64, 7, 16, 4)[:, :, 7:] == 0).all()) and w7.shape == (64, 3, 7, 7)
+
+
+def test_deeplab_rate56_is_its_centre_tap():
+    x = torch.randn(2, 8, 28, 28)
+    w = torch.randn(4, 8, 3, 3)
+    assert torch.allclose(F.conv2d(x, w, padding=56, dilation=56), F.conv2d(x, w[:, :, 1:2, 1:2]), atol=1e-5)   # deeplab.py:35
+
+
+# ------------------------------------------------------------------------------------------- predictor module
+def test_predictor_scripts_saves_and_fails_loudly_on_cpu():
+    from densepose_torchscript_b200 import synth
+    from densepose_torchscript_b200.config import BUILTIN
+    from densepose_torchscript_b200.predictor import DensePoseB200Predictor
+    spec = BUILTIN["densepose_rcnn_R_50_FPN_s1x_legacy"]
+    pred = DensePoseB200Predictor(spec, synth.add_aliases(synth.make_state_dict(spec, 0), spec)).eval()
+    scripted = torch.jit.script(pred)
+    assert "Tensor original_image, bool bgr=True) -> Dict(str, Tensor)" in str(scripted.forward.schema)
+    buf = io.BytesIO()
+    torch.jit.save(scripted, buf)
+    buf.seek(0)
+    loaded = torch.jit.load(buf).eval().half()
+    assert (loaded.min_size, loaded.max_size, loaded.input_format) == (800, 1333, "BGR")
+    assert loaded.dtype_probe.dtype == torch.float16 and loaded.weights.dtype == torch.uint8
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception, match="no CPU implementation"):
+            loaded(torch.zeros(8, 8, 3))
+
+
+# ------------------------------------------------------------------------------------------- sharding
+def test_shard_indices_cover_everything_once():
+    from densepose_torchscript_b200.parallel import shard_indices
+    for n in (0, 1, 7, 64, 65):
+        for world in (1, 2, 8):
+            for block in (1, 4, 8):
+                seen = sorted(i for r in range(world) for i in shard_indices(n, r, world, block))
+                assert seen == list(range(n))
+    assert shard_indices(20, 1, 2, 4) == [4, 5, 6, 7, 12, 13, 14, 15]
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from densepose_torchscript_b200.parallel import run_sharded
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+items = list(range(37))
+calls = []
+def process(batch):
+    calls.append(len(batch))
+    return [{"frame": x, "rank": dist.get_rank(), "sq": x * x} for x in batch]
+res = run_sharded(items, process, batch=4)
+if dist.get_rank() == 0:
+    assert [r["frame"] for r in res] == items and all(r["sq"] == r["frame"] ** 2 for r in res)
+    assert {r["rank"] for r in res} == {0, 1}
+    print("SHARD_OK", sum(1 for r in res if r["rank"] == 1))
+else:
+    assert res is None
+assert max(calls) <= 4
+dist.destroy_process_group()
+"""
+
+
+def test_run_sharded_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "SHARD_OK 17" in outs[0][0]
