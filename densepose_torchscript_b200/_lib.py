@@ -133,6 +133,7 @@ _proto("dpb200_session_workspace_bytes", C.c_size_t, [vp, i32, i32, i32])
 _proto("dpb200_session_create", C.c_int, [vp, i32, i32, i32, i32, vp, C.c_size_t, C.POINTER(vp)])
 _proto("dpb200_session_destroy", None, [vp])
 _proto("dpb200_session_run", C.c_int, [vp, C.POINTER(ForwardIO), vp])
+_proto("dpb200_session_set_graph", C.c_int, [vp, i32])
 _proto("dpb200_session_launch_count", C.c_int, [vp])
 _proto("dpb200_session_flops", C.c_double, [vp])
 _proto("dpb200_session_op_info", C.c_int, [vp, i32, C.c_char_p, i32, C.POINTER(C.c_double)])
@@ -145,7 +146,7 @@ EXPORTS = [
     "dpb200_maxpool3x3s2", "dpb200_upsample2x", "dpb200_decoder_merge", "dpb200_rpn_proposals",
     "dpb200_nms_sorted", "dpb200_roi_align", "dpb200_box_predict", "dpb200_groupnorm_relu", "dpb200_avgpool",
     "dpb200_predictor_upsample", "dpb200_dp_resample", "dpb200_model_create", "dpb200_model_destroy",
-    "dpb200_session_workspace_bytes", "dpb200_session_create", "dpb200_session_destroy", "dpb200_session_run",
+    "dpb200_session_workspace_bytes", "dpb200_session_create", "dpb200_session_destroy", "dpb200_session_run", "dpb200_session_set_graph",
     "dpb200_session_launch_count", "dpb200_session_flops", "dpb200_session_op_info", "dpb200_session_profile", "dpb200_session_geometry", "dpb200_session_tap",
 ]
 

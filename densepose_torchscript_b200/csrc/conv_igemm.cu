@@ -479,13 +479,20 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
   return 0;
 }
 
+int conv_kernels_init() {
+  cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) { set_error("conv: smem attr: %s", cudaGetErrorString(e)); return -3; }
+  return 0;
+}
+
 int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
-  static int smem_set = 0;
-  if (smem_set < plan.smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { set_error("conv: smem attr: %s", cudaGetErrorString(e)); return -3; }
-    smem_set = 227 * 1024;
+  static thread_local int init_dev = -1;     // per host thread: the device the attribute was last set on
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (init_dev != dev) {
+    if (conv_kernels_init()) return -3;
+    init_dev = dev;
   }
   conv_igemm_kernel<<<plan.grid, kThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.p);
   cudaError_t e = cudaGetLastError();

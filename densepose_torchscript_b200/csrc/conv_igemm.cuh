@@ -63,6 +63,8 @@ struct ConvPlan {
 // Host only; no GPU work. Returns 0 or a negative error (message via dpb::set_error).
 int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms);
 int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream);
+// Sets the opt-in shared-memory attribute of the conv kernel(s) on the current device (idempotent).
+int conv_kernels_init();
 
 void set_error(const char* fmt, ...);
 const char* get_error();

@@ -329,66 +329,111 @@ int launch_avgpool(const bf16* x, bf16* y, int R, int HW, int C, const int* n_va
 }
 
 // ------------------------------------------------------------------------------------ predictor tail
-// CTA (k, roi): stages low-res rows (k, k+1) in shared memory and writes output rows 2k+1, 2k+2 of every
-// channel plane with x-contiguous (coalesced) NCHW stores. k in [-1, S-1].
+// CTA (kb, roi) stages kPairs+1 consecutive low-res rows in shared memory (NHWC, as the deconv GEMM wrote them)
+// and writes the 2*kPairs output rows between them. Work item = (channel c, 8 output columns): lanes run
+// along c (conflict-free smem reads), every thread emits full 32-byte sectors of an NCHW plane.
+// Output row 2k+1 mixes low rows (k, k+1) with weights (.75, .25), row 2k+2 with (.25, .75); k = -1 and
+// k = S-1 collapse onto the edge row (ATen upsample_bilinear2d, align_corners=False, chart.py:62-74).
+static constexpr int kUpPairs = 3;
+
 __global__ void __launch_bounds__(256)
 predictor_upsample_kernel(const float* __restrict__ low, int S, int Cpad, int Kc,
                           const int* __restrict__ n_valid, float* __restrict__ coarse,
                           float* __restrict__ fine, float* __restrict__ u, float* __restrict__ v) {
   const int r = blockIdx.y;
   if (n_valid != nullptr && r >= *n_valid) return;
-  const int k = (int)blockIdx.x - 1;
-  const int r0 = k < 0 ? 0 : k, r1 = (k + 1 > S - 1) ? S - 1 : k + 1;
-  extern __shared__ float sm[];            // [2][S][Cs]
-  const int Cs = Cpad + 1;                 // padded channel stride: conflict-free column reads
-  const float* src0 = low + ((long long)r * S + r0) * S * Cpad;
-  const float* src1 = low + ((long long)r * S + r1) * S * Cpad;
-  for (int i = threadIdx.x; i < S * Cpad; i += blockDim.x) {
-    const int xx = i / Cpad, c = i - xx * Cpad;
-    sm[xx * Cs + c] = __ldg(src0 + i);
-    sm[(S + xx) * Cs + c] = __ldg(src1 + i);
+  const int k0 = (int)blockIdx.x * kUpPairs - 1;           // first pair index handled here
+  extern __shared__ __align__(16) float sm[];              // [kUpPairs + 1][S][Cpad]
+  const int row_elems = S * Cpad;
+  for (int j = 0; j <= kUpPairs; ++j) {
+    int ry = k0 + j;
+    ry = ry < 0 ? 0 : (ry > S - 1 ? S - 1 : ry);
+    const float4* src = reinterpret_cast<const float4*>(low + ((long long)r * S + ry) * row_elems);
+    float4* dst = reinterpret_cast<float4*>(sm + j * row_elems);
+    for (int i = threadIdx.x; i < row_elems / 4; i += blockDim.x) dst[i] = __ldg(src + i);
   }
   __syncthreads();
   const int So = 2 * S;
   const int C = Kc + 75;
-  for (int half = 0; half < 2; ++half) {
-    const int oy = 2 * k + 1 + half;
-    if (oy < 0 || oy >= So) continue;
-    // oy = 2k+1: rows (k, k+1) weights (0.75, 0.25); oy = 2k+2: weights (0.25, 0.75); edges collapse.
-    int y0, y1; float ly;
-    up2_index(oy, S, y0, y1, ly);
-    const int s0 = (y0 == r0) ? 0 : 1, s1 = (y1 == r0) ? 0 : 1;
-    const float hy = 1.f - ly;
-    for (int i = threadIdx.x; i < C * So; i += blockDim.x) {
-      const int c = i / So, ox = i - c * So;
-      int x0, x1; float lx;
-      up2_index(ox, S, x0, x1, lx);
-      const float hx = 1.f - lx;
-      const float v00 = sm[(s0 * S + x0) * Cs + c], v01 = sm[(s0 * S + x1) * Cs + c];
-      const float v10 = sm[(s1 * S + x0) * Cs + c], v11 = sm[(s1 * S + x1) * Cs + c];
-      const float val = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
-      float* dst; int cc, nc;
-      if (c < Kc) { dst = coarse; cc = c; nc = Kc; }
-      else if (c < Kc + 25) { dst = fine; cc = c - Kc; nc = 25; }
-      else if (c < Kc + 50) { dst = u; cc = c - Kc - 25; nc = 25; }
-      else { dst = v; cc = c - Kc - 50; nc = 25; }
-      dst[(((long long)r * nc + cc) * So + oy) * So + ox] = val;
+  const int items = C * (S / 4);
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int g = it / C, c = it - g * C;
+    float* dst; int cc, nc;
+    if (c < Kc) { dst = coarse; cc = c; nc = Kc; }
+    else if (c < Kc + 25) { dst = fine; cc = c - Kc; nc = 25; }
+    else if (c < Kc + 50) { dst = u; cc = c - Kc - 25; nc = 25; }
+    else { dst = v; cc = c - Kc - 50; nc = 25; }
+    float* plane = dst + ((long long)r * nc + cc) * So * So + 8 * g;
+    const int xm = 4 * g - 1 < 0 ? 0 : 4 * g - 1;
+    const int xp = 4 * g + 4 > S - 1 ? S - 1 : 4 * g + 4;
+    // horizontal pass per staged row: h[j][t] = (1-lx_t) * v[x0_t] + lx_t * v[x1_t]
+    float a[6], lo[8], hi[8];
+    const float lx0 = (g == 0) ? 0.f : 0.75f;               // output column 0 clamps to the edge
+    auto hrow = [&](int j, float* h) {
+      const float* p = sm + j * row_elems + c;
+      a[0] = p[xm * Cpad];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) a[1 + t] = p[(4 * g + t) * Cpad];
+      a[5] = p[xp * Cpad];
+      h[0] = (1.f - lx0) * a[0] + lx0 * a[1];
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        h[1 + 2 * t] = 0.75f * a[1 + t] + 0.25f * a[2 + t];
+        h[2 + 2 * t] = 0.25f * a[1 + t] + 0.75f * a[2 + t];
+      }
+      h[7] = 0.75f * a[4] + 0.25f * a[5];
+    };
+    hrow(0, lo);
+#pragma unroll
+    for (int j = 0; j < kUpPairs; ++j) {
+      const int k = k0 + j;
+      if (k > S - 1) break;
+      hrow(j + 1, hi);
+      if (k >= 0) {                                         // row 2k+1: (.75, .25)
+        float o[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = 0.75f * lo[t] + 0.25f * hi[t];
+        float4* q = reinterpret_cast<float4*>(plane + (long long)(2 * k + 1) * So);
+        q[0] = make_float4(o[0], o[1], o[2], o[3]);
+        q[1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+      if (k < S - 1) {                                      // row 2k+2: (.25, .75); k = -1 -> row 0 = edge row
+        float o[8];
+        const float ly = (k < 0) ? 0.f : 0.75f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = (1.f - ly) * lo[t] + ly * hi[t];
+        float4* q = reinterpret_cast<float4*>(plane + (long long)(2 * k + 2) * So);
+        q[0] = make_float4(o[0], o[1], o[2], o[3]);
+        q[1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) lo[t] = hi[t];
     }
   }
 }
 
+static constexpr size_t kUpMaxSmem = 96 * 1024;
+int stage_kernels_init() {
+  cudaError_t e = cudaFuncSetAttribute(predictor_upsample_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpMaxSmem);
+  if (e != cudaSuccess) { set_error("predictor_upsample smem attr: %s", cudaGetErrorString(e)); return -3; }
+  return 0;
+}
+
 int launch_predictor_upsample(const float* low, int R, int S, int Cpad, int Kc, const int* n_valid,
                               float* coarse, float* fine, float* u, float* v, cudaStream_t s) {
-  const size_t smem = (size_t)2 * S * (Cpad + 1) * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem_set < smem) {
-    cudaError_t e = cudaFuncSetAttribute(predictor_upsample_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("predictor_upsample smem: %s", cudaGetErrorString(e)); return -3; }
-    smem_set = smem;
+  if (S % 4 || Cpad % 4 || Kc + 75 > Cpad) { set_error("predictor_upsample: bad shape S %d Cpad %d", S, Cpad); return -1; }
+  const size_t smem = (size_t)(kUpPairs + 1) * S * Cpad * sizeof(float);
+  if (smem > kUpMaxSmem) { set_error("predictor_upsample: S %d Cpad %d needs %zu B of shared memory", S, Cpad, smem); return -1; }
+  static thread_local int init_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (init_dev != dev) {
+    if (stage_kernels_init()) return -3;
+    init_dev = dev;
   }
   if (R == 0) return 0;
-  dim3 grid(S + 1, R);
+  dim3 grid((S + 1 + kUpPairs - 1) / kUpPairs, R);
   predictor_upsample_kernel<<<grid, 256, smem, s>>>(low, S, Cpad, Kc, n_valid, coarse, fine, u, v);
   DPB_CHECK_LAUNCH("predictor_upsample");
   return 0;

@@ -105,6 +105,9 @@ int launch_avgpool(const bf16* x, bf16* y, int R, int HW, int C, const int* n_va
 int launch_predictor_upsample(const float* low, int R, int S, int Cpad, int Kc, const int* n_valid,
                               float* coarse, float* fine, float* u, float* v, cudaStream_t s);
 
+// Opt-in shared-memory attributes of the stage kernels on the current device (idempotent).
+int stage_kernels_init();
+
 // ---- per-box DensePose resample (visualizer.py:10-56) -------------------------------------------
 struct ResampleArgs {
   const float* coarse; const float* fine; const float* u; const float* v;   // [D, C, S, S] fp32

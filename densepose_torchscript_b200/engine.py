@@ -43,6 +43,12 @@ class Session:
         self.io.det_count = self.det_count.data_ptr(); self.io.det_offsets = self.det_offsets.data_ptr()
         self.io.coarse = self.coarse.data_ptr(); self.io.fine = self.fine.data_ptr()
         self.io.u = self.u.data_ptr(); self.io.v = self.v.data_ptr()
+        # launches go to a private stream (the legacy default stream cannot be graph-captured); run() orders
+        # it after / before the caller's current stream with events, so the semantics stay "enqueued on the
+        # current stream"
+        self.stream = torch.cuda.Stream(device=dev)
+        self.use_graph = engine.use_graph
+        check(lib.dpb200_session_set_graph(self.handle, int(self.use_graph)), "dpb200_session_set_graph")
         g = (C.c_int32 * 4)()
         lib.dpb200_session_geometry(self.handle, C.byref(g))
         self.hr, self.wr, self.hp, self.wp = g[0], g[1], g[2], g[3]
@@ -64,8 +70,14 @@ class Session:
         assert images.dtype == (torch.uint8 if self.src_u8 else torch.float32)
         self.io.images = images.data_ptr()
         self.io.bgr = int(bgr)
-        check(lib.dpb200_session_run(self.handle, C.byref(self.io), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+        cur = torch.cuda.current_stream()
+        if not self.use_graph:
+            check(lib.dpb200_session_run(self.handle, C.byref(self.io), C.c_void_p(cur.cuda_stream)), "dpb200_session_run")
+            return
+        self.stream.wait_stream(cur)
+        check(lib.dpb200_session_run(self.handle, C.byref(self.io), C.c_void_p(self.stream.cuda_stream)),
               "dpb200_session_run")
+        cur.wait_stream(self.stream)
 
     def op_info(self) -> List[Tuple[str, float]]:
         out = []
@@ -121,9 +133,11 @@ class Engine:
     """Packed weights + native model handle on one CUDA device."""
 
     def __init__(self, spec: ModelSpec, state_dict: Optional[Dict[str, torch.Tensor]] = None,
-                 packed: Optional[Dict[str, Packed]] = None, device: Optional[torch.device] = None):
+                 packed: Optional[Dict[str, Packed]] = None, device: Optional[torch.device] = None,
+                 use_graph: bool = True):
         _lib.require_device()
         self.spec = spec
+        self.use_graph = use_graph
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         if packed is None:
             if state_dict is None:

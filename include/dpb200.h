@@ -197,6 +197,11 @@ typedef struct dpb200_forward_io {
   float* v;                 /* [B*dets_per_image, 25, 4S, 4S]                                     */
 } dpb200_forward_io;
 int dpb200_session_run(dpb200_session* s, const dpb200_forward_io* io, void* stream);
+/* enable != 0: dpb200_session_run captures its launch sequence into a CUDA graph the first time it sees an
+ * io binding (all pointers + bgr) and replays the instantiated graph afterwards (one host call instead of
+ * ~110 launches; instantiation is the only hidden allocation in the library). `stream` must then be a real
+ * stream: on the legacy default stream (NULL) the kernels are launched directly. */
+int dpb200_session_set_graph(dpb200_session* s, int32_t enable);
 
 /* Kernel launches one run enqueues, and their algorithmic FLOPs (2*MAC of every conv/linear at full
  * detection capacity). */
