@@ -181,7 +181,7 @@ def run_ours(a):
     import torch.distributed as dist
     from densepose_torchscript_b200 import synth
     from densepose_torchscript_b200.config import BUILTIN
-    from densepose_torchscript_b200.engine import Engine
+    from densepose_torchscript_b200.engine import Engine, HostPipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -224,28 +224,59 @@ def run_ours(a):
     ms_dev = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- e2e: pinned host images in, reference-format outputs back to pinned host memory, every step
-    outs_dev = [sess.pred_boxes, sess.scores, sess.det_count, sess.det_offsets, sess.coarse, sess.fine, sess.u, sess.v]
-    outs_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs_dev]
-    h2d = host.numel() * host.element_size()
-    d2h = sum(t.numel() * t.element_size() for t in outs_dev)
-
-    def e2e_step():
-        images.copy_(host, non_blocking=True)
-        sess.run(images)
-        for hbuf, dbuf in zip(outs_host, outs_dev):
-            hbuf.copy_(dbuf, non_blocking=True)
-
-    for _ in range(2):
-        e2e_step()
+    # ---- e2e: the public host-in / host-out API (HostPipeline): every step copies the pinned host images to the
+    # device, runs the forward and copies boxes, scores, counts and all four DensePose tensors back to pinned
+    # host memory; two slots, so the PCIe copies of one step overlap the kernels of the next
+    pipe = HostPipeline(eng, B, H, W, False, depth=2)
+    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
+    for _ in range(3):
+        pipe.submit(host)
+    pipe.drain()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
+    for sl in pipe.slots:
+        sl["sess"].stream.wait_stream(torch.cuda.current_stream())
+    got = 0
     for _ in range(a.steps):
-        e2e_step()
+        r = pipe.submit(host)
+        got += 0 if r is None else len(r)
+    for r in pipe.drain():
+        got += len(r)
+    for sl in pipe.slots:
+        torch.cuda.current_stream().wait_stream(sl["sess"].stream)
     e3.record()
     barrier()
+    assert got == B * a.steps, (got, B, a.steps)
     ms_e2e = e2.elapsed_time(e3)
+
+    # ---- p50 batch-1 latency (BASELINE.json's second metric): one image, host in -> host out, synchronous
+    lat = None
+    if world == 1 and not a.no_latency:
+        pipe1 = HostPipeline(eng, 1, H, W, False, depth=1)
+        one = host[:1].clone().pin_memory()
+        ts, ts_dev = [], []
+        s1 = pipe1.slots[0]["sess"]
+        dev1 = pipe1.slots[0]["dev_in"]
+        for i in range(5 + 30):
+            t0 = time.perf_counter()
+            pipe1.submit(one)
+            pipe1.drain()
+            if i >= 5:
+                ts.append((time.perf_counter() - t0) * 1e3)
+        for i in range(3 + 30):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            s1.run(dev1)
+            ev1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts_dev.append(ev0.elapsed_time(ev1))
+        ts.sort(); ts_dev.sort()
+        lat = {"p50_ms": ts[len(ts) // 2], "p90_ms": ts[int(len(ts) * 0.9)], "device_only_p50_ms": ts_dev[len(ts_dev) // 2],
+               "samples": len(ts), "d2h_bytes": pipe1.d2h_bytes,
+               "note": "batch 1, pinned host image in, all outputs back in pinned host memory, wall clock around submit+drain"}
+        del pipe1
 
     # ---- per-launch profile (CUDA events on the launch stream) for the roofline of the dominant kernel
     info = sess.op_info()
@@ -286,8 +317,9 @@ def run_ours(a):
                        "l2": f"per-step working set {sess.workspace.numel() / 1e9:.1f} GB >> 126 MB L2 (no flush needed)"},
             "e2e": {"value": n_img / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / a.steps,
-                    "note": "pinned host fp32 images in; boxes, scores, counts and all four DensePose tensors (full "
-                            "capacity) copied to pinned host memory every step"},
+                    "note": "HostPipeline (public API), 2 slots: pinned host fp32 images in; boxes, scores, counts and all "
+                            "four fp32 DensePose tensors (full capacity) copied to pinned host memory every step; "
+                            "PCIe D2H of step i overlaps the kernels of step i+1"},
             "gpu_launches": sess.launches * a.steps,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
@@ -298,6 +330,8 @@ def run_ours(a):
                          "step_tflops": gflop_step / (ms_dev / a.steps)},
             "top_launches_ms": [[round(ms, 4), n] for ms, n in top],
         }
+        if lat is not None:
+            line["latency_batch1"] = lat
         if world == 1 and not a.no_cpu_baseline:
             rate, sec, threads, cdets, _ = cpu_reference_rate(H, W, 1, 0, a.config)
             line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
@@ -319,6 +353,7 @@ def main():
     ap.add_argument("--height", type=int, default=800)
     ap.add_argument("--width", type=int, default=1333)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--profile-out", default="", help="write the per-launch ms profile (JSON) here")
     a = ap.parse_args()
     if a.impl == "reference":

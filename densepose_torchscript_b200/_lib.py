@@ -39,6 +39,7 @@ class Conv2dArgs(C.Structure):
         ("res", vp), ("res_sn", i64), ("res_sy", i64), ("res_sx", i64), ("res_shift", i32),
         ("y", vp), ("y_fp32", i32), ("y_sn", i64), ("y_sy", i64), ("y_sx", i64),
         ("n_valid", vp), ("block_n", i32), ("stages", i32), ("tiled", i32),
+        ("y_sc", i64), ("epilogue", i32),
     ]
 
 
@@ -125,7 +126,7 @@ _proto("dpb200_roi_align", C.c_int, [C.POINTER(RoiAlignArgs), vp])
 _proto("dpb200_box_predict", C.c_int, [C.POINTER(BoxPredictArgs), vp])
 _proto("dpb200_groupnorm_relu", C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp])
 _proto("dpb200_avgpool", C.c_int, [vp, vp, i32, i32, i32, vp, vp])
-_proto("dpb200_predictor_upsample", C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp])
+_proto("dpb200_predictor_upsample", C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp])
 _proto("dpb200_dp_resample", C.c_int, [C.POINTER(ResampleArgs), vp])
 _proto("dpb200_model_create", C.c_int, [C.POINTER(ModelConfig), C.POINTER(Weight), i32, C.POINTER(vp)])
 _proto("dpb200_model_destroy", None, [vp])

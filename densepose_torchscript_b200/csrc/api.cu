@@ -50,6 +50,8 @@ int dpb200_conv2d(const dpb200_conv2d_args* a, void* stream) {
   d.out_sn = a->y_sn ? a->y_sn : d.out_sy * a->h_out;
   d.n_valid = a->n_valid; d.block_n = a->block_n; d.stages = a->stages;
   d.im2col = a->tiled ? 0 : 1;
+  d.out_sc = a->y_sc > 0 ? a->y_sc : 1;
+  d.epilogue = a->epilogue;
   dpb::ConvPlan plan;
   int r = dpb::conv_plan_build(&plan, d, num_sms());
   if (r) return r;
@@ -131,8 +133,8 @@ int dpb200_avgpool(const void* x, void* y, int32_t r, int32_t hw, int32_t c, con
 }
 int dpb200_predictor_upsample(const float* low, int32_t r, int32_t s, int32_t cpad, int32_t kc,
                               const int32_t* n_valid, float* coarse, float* fine, float* u, float* v,
-                              void* stream) {
-  return launch_predictor_upsample(low, r, s, cpad, kc, n_valid, coarse, fine, u, v, S(stream));
+                              int32_t planar, void* stream) {
+  return launch_predictor_upsample(low, r, s, cpad, kc, n_valid, coarse, fine, u, v, planar, S(stream));
 }
 
 int dpb200_dp_resample(const dpb200_resample_args* a, void* stream) {

@@ -29,6 +29,8 @@ struct ConvDesc {
   void* out = nullptr;
   int out_fp32 = 0;
   long long out_sn = 0, out_sy = 0, out_sx = 0;   // output strides (elements)
+  long long out_sc = 1;                           // output channel stride; != 1: channel-planar fp32 output
+  int epilogue = 0;                               // 0 choose, 1 direct global stores, 2 smem slabs + TMA store
   const int* n_valid = nullptr;                   // device scalar: images actually present (<= N)
   int im2col = 1;                                 // A operand through im2col-mode TMA (else tiled boxes)
   int block_n = 0;                                // 0 = choose
@@ -42,18 +44,22 @@ struct ConvKParams {
   int H_out, W_out, N;
   int kh, kw, sx, sy, pad_x, pad_y, dil;
   int cin_chunks, stages, acc_stride;
+  int nslab, res_tma;                             // staged epilogue: slab ring size, residual through TMA
   int relu, out_fp32, res_shift, im2col;
   const float* bias;
   const __nv_bfloat16* res;
   long long res_sn, res_sy, res_sx;
   void* out;
-  long long out_sn, out_sy, out_sx;
+  long long out_sn, out_sy, out_sx, out_sc;
   const int* n_valid;
 };
 
 struct ConvPlan {
   alignas(64) CUtensorMap tmA;
   alignas(64) CUtensorMap tmB;
+  alignas(64) CUtensorMap tmOut;   // staged epilogue: [M, cout] bf16 view of the output
+  alignas(64) CUtensorMap tmRes;   // staged epilogue: [M, cout] bf16 view of the residual
+  int staged = 0;
   ConvKParams p;
   int grid = 0;
   int smem = 0;

@@ -75,25 +75,29 @@ static __device__ void nms_sorted_block(const float4* __restrict__ g_boxes, int 
   }
   __syncthreads();
   const int nw = (n + 31) >> 5;
-  for (int item = threadIdx.x; item < n * nw; item += blockDim.x) {
-    const int i = item / nw, w = item - i * nw;
-    uint32_t bits = 0;
-    const int j0 = w * 32;
-    if (j0 + 31 > i) {
+  {
+    // One warp per (row i, 32-column word w >= i/32): lane = column, the word is a ballot. Box reads are
+    // conflict-free (consecutive float4 per lane, row box broadcast from registers).
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int i = warp; i < n; i += nwarps) {
       const float4 bi = boxes[i];
       const float ai = areas[i];
-      const int jend = (j0 + 32 < n) ? j0 + 32 : n;
-      for (int j = (j0 > i + 1 ? j0 : i + 1); j < jend; ++j) {
-        const float4 bj = boxes[j];
-        const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
-        const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
-        const float w_ = fmaxf(0.f, __fsub_rn(xx2, xx1)), h_ = fmaxf(0.f, __fsub_rn(yy2, yy1));
-        const float inter = __fmul_rn(w_, h_);
-        const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, areas[j]), inter));
-        if (ovr > thr) bits |= 1u << (j - j0);
+      for (int w = i >> 5; w < nw; ++w) {
+        const int j = w * 32 + lane;
+        bool sup = false;
+        if (j > i && j < n) {
+          const float4 bj = boxes[j];
+          const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+          const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+          const float w_ = fmaxf(0.f, __fsub_rn(xx2, xx1)), h_ = fmaxf(0.f, __fsub_rn(yy2, yy1));
+          const float inter = __fmul_rn(w_, h_);
+          const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, areas[j]), inter));
+          sup = ovr > thr;
+        }
+        const uint32_t bits = __ballot_sync(0xffffffffu, sup);
+        if (lane == 0) mask[i * 32 + w] = bits;
       }
     }
-    mask[i * 32 + w] = bits;
   }
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -104,7 +108,7 @@ static __device__ void nms_sorted_block(const float4* __restrict__ g_boxes, int 
       const uint32_t r = __shfl_sync(0xffffffffu, removed, i >> 5);
       if (!((r >> (i & 31)) & 1u)) {
         if (lane == (i >> 5)) kept |= 1u << (i & 31);
-        if (lane < nw) removed |= mask[i * 32 + lane];
+        if (lane >= (i >> 5) && lane < nw) removed |= mask[i * 32 + lane];   // words left of the diagonal are never written
       }
     }
     alive_words[lane] = kept;

@@ -412,6 +412,74 @@ predictor_upsample_kernel(const float* __restrict__ low, int S, int Cpad, int Kc
   }
 }
 
+// Same operation on the phase-planar layout the deconv GEMM epilogue writes: low[r][py][px][c][S/2][S/2]
+// holds low-res pixel (2*yy+py, 2*xx+px). No shared memory: lanes run along x, so the loads (4 B, neighbouring
+// lanes adjacent) and the 16-byte stores are both coalesced; each thread walks kUpRows output-row pairs of
+// one 4-column strip and carries the horizontally interpolated row between them.
+static constexpr int kUpRows = 10;
+
+__global__ void __launch_bounds__(256)
+predictor_upsample_planar_kernel(const float* __restrict__ low, int S, int Cpad, int Kc,
+                                 const int* __restrict__ n_valid, float* __restrict__ coarse,
+                                 float* __restrict__ fine, float* __restrict__ u, float* __restrict__ v) {
+  const int r = blockIdx.y;
+  if (n_valid != nullptr && r >= *n_valid) return;
+  const int Sh = S >> 1, So = 2 * S;
+  const int G = S >> 1;                        // 4-column output strips per row
+  const int C = Kc + 75;
+  const int KB = (S + 1 + kUpRows - 1) / kUpRows;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= KB * C * G) return;
+  const int g = item % G;
+  const int c = (item / G) % C;
+  const int kb = item / (G * C);
+  float* dst; int cc, nc;
+  if (c < Kc) { dst = coarse; cc = c; nc = Kc; }
+  else if (c < Kc + 25) { dst = fine; cc = c - Kc; nc = 25; }
+  else if (c < Kc + 50) { dst = u; cc = c - Kc - 25; nc = 25; }
+  else { dst = v; cc = c - Kc - 50; nc = 25; }
+  float* plane = dst + ((long long)r * nc + cc) * So * So + 4 * g;
+  const long long plane_sz = (long long)Sh * Sh;
+  const float* lr = low + ((long long)r * 4 * Cpad + c) * plane_sz;     // + (py*2+px)*Cpad*plane_sz
+  // low columns 2g-1, 2g, 2g+1, 2g+2 (clamped): (phase px, column xx) of each
+  const int xa = g == 0 ? 0 : g - 1, pa = g == 0 ? 0 : 1;
+  const int xd = g == G - 1 ? Sh - 1 : g + 1, pd = g == G - 1 ? 1 : 0;
+  const float lx0 = (g == 0) ? 0.f : 0.75f;    // output column 0 clamps to the edge
+  auto hrow = [&](int y, float* h) {
+    y = y < 0 ? 0 : (y > S - 1 ? S - 1 : y);
+    const float* p0 = lr + (long long)((y & 1) * 2) * Cpad * plane_sz + (long long)(y >> 1) * Sh;
+    const float* p1 = p0 + (long long)Cpad * plane_sz;
+    const float a0 = __ldg((pa ? p1 : p0) + xa), a1 = __ldg(p0 + g), a2 = __ldg(p1 + g),
+                a3 = __ldg((pd ? p1 : p0) + xd);
+    h[0] = (1.f - lx0) * a0 + lx0 * a1;
+    h[1] = 0.75f * a1 + 0.25f * a2;
+    h[2] = 0.25f * a1 + 0.75f * a2;
+    h[3] = 0.75f * a2 + 0.25f * a3;
+  };
+  const int k0 = kb * kUpRows - 1;
+  float lo[4], hi[4];
+  hrow(k0, lo);
+#pragma unroll
+  for (int j = 0; j < kUpRows; ++j) {
+    const int k = k0 + j;
+    if (k > S - 1) break;
+    hrow(k + 1, hi);
+    if (k >= 0) {
+      *reinterpret_cast<float4*>(plane + (long long)(2 * k + 1) * So) =
+          make_float4(0.75f * lo[0] + 0.25f * hi[0], 0.75f * lo[1] + 0.25f * hi[1],
+                      0.75f * lo[2] + 0.25f * hi[2], 0.75f * lo[3] + 0.25f * hi[3]);
+    }
+    if (k < S - 1) {
+      const float ly = (k < 0) ? 0.f : 0.75f, hy = 1.f - ly;
+      *reinterpret_cast<float4*>(plane + (long long)(2 * k + 2) * So) =
+          make_float4(hy * lo[0] + ly * hi[0], hy * lo[1] + ly * hi[1], hy * lo[2] + ly * hi[2],
+                      hy * lo[3] + ly * hi[3]);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) lo[t] = hi[t];
+  }
+}
+
 static constexpr size_t kUpMaxSmem = 96 * 1024;
 int stage_kernels_init() {
   cudaError_t e = cudaFuncSetAttribute(predictor_upsample_kernel,
@@ -421,7 +489,17 @@ int stage_kernels_init() {
 }
 
 int launch_predictor_upsample(const float* low, int R, int S, int Cpad, int Kc, const int* n_valid,
-                              float* coarse, float* fine, float* u, float* v, cudaStream_t s) {
+                              float* coarse, float* fine, float* u, float* v, int planar, cudaStream_t s) {
+  if (planar) {
+    if (S % 2 || Kc + 75 > Cpad) { set_error("predictor_upsample: bad shape S %d Cpad %d", S, Cpad); return -1; }
+    if (R == 0) return 0;
+    const int KB = (S + 1 + kUpRows - 1) / kUpRows;
+    const int items = KB * (Kc + 75) * (S / 2);
+    dim3 grid((items + 255) / 256, R);
+    predictor_upsample_planar_kernel<<<grid, 256, 0, s>>>(low, S, Cpad, Kc, n_valid, coarse, fine, u, v);
+    DPB_CHECK_LAUNCH("predictor_upsample_planar");
+    return 0;
+  }
   if (S % 4 || Cpad % 4 || Kc + 75 > Cpad) { set_error("predictor_upsample: bad shape S %d Cpad %d", S, Cpad); return -1; }
   const size_t smem = (size_t)(kUpPairs + 1) * S * Cpad * sizeof(float);
   if (smem > kUpMaxSmem) { set_error("predictor_upsample: S %d Cpad %d needs %zu B of shared memory", S, Cpad, smem); return -1; }

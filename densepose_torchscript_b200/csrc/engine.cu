@@ -107,7 +107,7 @@ struct Builder {
     const int* n_valid = nullptr;
     int kh = 0, kw = 0, pad_y = -1, pad_x = -1, sy = 0, sx = 0;       // overrides
     long long x_sw = 0, x_sh = 0, x_sn = 0;                           // input stride overrides (elements)
-    long long out_sn = 0, out_sy = 0, out_sx = 0; long long out_off = 0;   // output view overrides
+    long long out_sn = 0, out_sy = 0, out_sx = 0, out_sc = 0; long long out_off = 0;   // output view overrides
     int H_out = 0, W_out = 0;
     bool no_bias = false;
   };
@@ -139,6 +139,7 @@ struct Builder {
     d.out_sx = o.out_sx ? o.out_sx : y.C;
     d.out_sy = o.out_sy ? o.out_sy : d.out_sx * y.W;
     d.out_sn = o.out_sn ? o.out_sn : d.out_sy * y.H;
+    d.out_sc = o.out_sc ? o.out_sc : 1;
     d.out = y.fp32 ? (void*)(reinterpret_cast<float*>(y.p) + o.out_off)
                    : (void*)(reinterpret_cast<bf16*>(y.p) + o.out_off);
     d.n_valid = o.n_valid;
@@ -459,26 +460,28 @@ int build_plan(dpb200_session* s) {
     head_out = x;
   }
   b.tap("dp_head", head_out);
-  // ---- a18 predictor: ConvTranspose2d(k4,s2,p1) as four 2x2 phase convs, then bilinear x2 -> NCHW fp32
+  // ---- a18 predictor: ConvTranspose2d(k4,s2,p1) as four 2x2 phase convs, then bilinear x2 -> NCHW fp32.
+  // Output pixel (2y+py, 2x+px) of the deconv only depends on phase (py,px): each phase GEMM writes its
+  // own channel-planar fp32 block low[r][py][px][c][P][P] (TMEM lane = pixel, so planar stores coalesce).
   const int Cp = round_up(cfg.coarse_ch + 75, 16);
   const int S2 = 2 * P;
-  T4 low = b.act(Rd, S2, S2, Cp, 1);
+  T4 low = b.act(Rd, 4 * Cp, P, P, 1);      // [Rd][2][2][Cp][P][P]
   s->low = (float*)low.p; s->low_S = S2; s->low_C = Cp;
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
       Builder::ConvOpt o; o.k = 2; o.pad_y = py == 0 ? 1 : 0; o.pad_x = px == 0 ? 1 : 0; o.n_valid = nv;
       o.H_out = P; o.W_out = P;
-      o.out_sx = 2LL * Cp; o.out_sy = 2LL * S2 * Cp; o.out_sn = (long long)S2 * S2 * Cp;
-      o.out_off = ((long long)py * S2 + px) * Cp;
+      o.out_sx = 1; o.out_sy = P; o.out_sc = (long long)P * P; o.out_sn = 4LL * Cp * P * P;
+      o.out_off = (long long)(py * 2 + px) * Cp * P * P;
       b.conv("roi_heads.densepose_predictor.phase" + std::to_string(py * 2 + px), head_out, low, o);
     }
-  b.tap("dp_lowres", low);
+  b.tap_raw("dp_lowres", low.p, Rd, 4, Cp, P * P, 1);
   {
     dpb200_session* ss = s;
     const int Kc = cfg.coarse_ch;
     b.op([ss, Rd, Kc, nv](cudaStream_t st) {
       return launch_predictor_upsample(ss->low, Rd, ss->low_S, ss->low_C, Kc, nv, ss->io->coarse, ss->io->fine,
-                                       ss->io->u, ss->io->v, st);
+                                       ss->io->u, ss->io->v, 1, st);
     }, "predictor_upsample");
   }
   return b.fail;

@@ -166,7 +166,7 @@ class Engine:
         with torch.cuda.device(self.device):
             check(lib.dpb200_model_create(C.byref(cfg), arr, len(packed), C.byref(h)), "dpb200_model_create")
         self.handle = h
-        self._sessions: Dict[Tuple[int, int, int, bool], Session] = {}
+        self._sessions: Dict[Tuple[int, int, int, bool, int], Session] = {}
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -175,8 +175,9 @@ class Engine:
             lib.dpb200_model_destroy(h)
             self.handle = None
 
-    def session(self, batch: int, h0: int, w0: int, src_u8: bool = False) -> Session:
-        key = (batch, h0, w0, src_u8)
+    def session(self, batch: int, h0: int, w0: int, src_u8: bool = False, slot: int = 0) -> Session:
+        """`slot` > 0 gives additional independent sessions (own workspace, outputs, stream) of the same shape."""
+        key = (batch, h0, w0, src_u8, slot)
         s = self._sessions.get(key)
         if s is None:
             with torch.cuda.device(self.device):
@@ -193,3 +194,82 @@ class Engine:
         with torch.cuda.device(self.device):
             s.run(images, bgr)
         return s.results()
+
+
+class HostPipeline:
+    """Host-in / host-out serving loop: `depth` sessions of one shape, each with its own stream and pinned
+    staging buffers, so the PCIe copies of one batch overlap the kernels of the next.
+
+        pipe = HostPipeline(engine, batch, h0, w0)
+        for frames in batches:            # frames: [B,H,W,3] host tensor (pinned or not)
+            done = pipe.submit(frames)    # results of the batch submitted `depth` calls ago (or None)
+        tail = pipe.drain()
+
+    Every submit() enqueues H2D copy -> forward -> D2H copy of the reference-format outputs on the slot's
+    stream. Returned host tensors are views of the slot's pinned buffers: valid until that slot is reused.
+    """
+
+    def __init__(self, engine: Engine, batch: int, h0: int, w0: int, src_u8: bool = False, depth: int = 2):
+        self.engine, self.depth = engine, depth
+        self.slots = []
+        dt = torch.uint8 if src_u8 else torch.float32
+        with torch.cuda.device(engine.device):
+            for i in range(depth):
+                sess = engine.session(batch, h0, w0, src_u8, slot=i + 1)
+                dev_in = torch.empty(batch, h0, w0, 3, dtype=dt, device=engine.device)
+                host_in = torch.empty(batch, h0, w0, 3, dtype=dt).pin_memory()
+                outs_dev = [sess.pred_boxes, sess.scores, sess.det_count, sess.det_offsets, sess.coarse, sess.fine,
+                            sess.u, sess.v]
+                outs_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs_dev]
+                self.slots.append(dict(sess=sess, dev_in=dev_in, host_in=host_in, outs_dev=outs_dev,
+                                       outs_host=outs_host, done=torch.cuda.Event(), busy=False))
+        self.h2d_bytes = self.slots[0]["host_in"].numel() * self.slots[0]["host_in"].element_size()
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.slots[0]["outs_host"])
+        self._next = 0
+
+    def _collect(self, sl) -> Optional[List[Dict[str, torch.Tensor]]]:
+        if not sl["busy"]:
+            return None
+        sl["done"].synchronize()
+        sl["busy"] = False
+        boxes, scores, counts, offs, coarse, fine, u, v = sl["outs_host"]
+        sess = sl["sess"]
+        out = []
+        for b in range(sess.batch):
+            d, o = int(counts[b]), int(offs[b])
+            out.append({"image_size": torch.tensor([sess.h0, sess.w0], dtype=torch.int64),
+                        "pred_boxes": boxes[b, :d], "scores": scores[b, :d],
+                        "pred_classes": torch.zeros(d, dtype=torch.int64),
+                        "pred_densepose_coarse_segm": coarse[o:o + d], "pred_densepose_fine_segm": fine[o:o + d],
+                        "pred_densepose_u": u[o:o + d], "pred_densepose_v": v[o:o + d]})
+        return out
+
+    def submit(self, images: torch.Tensor, bgr: bool = True):
+        """Enqueue one host batch; returns the finished results of the slot being reused (None at start-up).
+        A pinned `images` tensor is copied to the device directly (the caller keeps it unchanged until the
+        results come back); pageable memory goes through the slot's pinned staging buffer first."""
+        sl = self.slots[self._next]
+        self._next = (self._next + 1) % self.depth
+        prev = self._collect(sl)
+        src = images
+        if not images.is_pinned():
+            sl["host_in"].copy_(images)
+            src = sl["host_in"]
+        sess = sl["sess"]
+        with torch.cuda.device(self.engine.device), torch.cuda.stream(sess.stream):
+            sl["dev_in"].copy_(src, non_blocking=True)
+            sess.run(sl["dev_in"], bgr)
+            for hbuf, dbuf in zip(sl["outs_host"], sl["outs_dev"]):
+                hbuf.copy_(dbuf, non_blocking=True)
+            sl["done"].record(sess.stream)
+        sl["busy"] = True
+        return prev
+
+    def drain(self) -> List[List[Dict[str, torch.Tensor]]]:
+        out = []
+        for i in range(self.depth):
+            sl = self.slots[(self._next + i) % self.depth]
+            r = self._collect(sl)
+            if r is not None:
+                out.append(r)
+        return out

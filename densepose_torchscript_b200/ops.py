@@ -45,8 +45,10 @@ def conv2d(x: torch.Tensor, packed: torch.Tensor, bias: Optional[torch.Tensor], 
            stride: int = 1, pad: int = 0, dil: int = 1, relu: bool = False,
            res: Optional[torch.Tensor] = None, res_shift: int = 0, out_fp32: bool = False,
            n_valid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-           block_n: int = 0, stages: int = 0, tiled: bool = False) -> torch.Tensor:
-    """x: bf16 NHWC [N,H,W,Cin] (contiguous). Returns NHWC [N,Ho,Wo,cout_pad] bf16 (or fp32)."""
+           block_n: int = 0, stages: int = 0, tiled: bool = False, epilogue: int = 0,
+           planar: bool = False) -> torch.Tensor:
+    """x: bf16 NHWC [N,H,W,Cin] (contiguous). Returns NHWC [N,Ho,Wo,cout_pad] bf16 (or fp32); with
+    planar=True the fp32 result is channel-planar [N,cout_pad,Ho,Wo]."""
     _lib.require_device()
     assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
     n, h, w, cin = x.shape
@@ -55,8 +57,8 @@ def conv2d(x: torch.Tensor, packed: torch.Tensor, bias: Optional[torch.Tensor], 
     ho = (h + 2 * pad - dil * (kh - 1) - 1) // stride + 1
     wo = (w + 2 * pad - dil * (kw - 1) - 1) // stride + 1
     if out is None:
-        out = torch.empty(n, ho, wo, cout_pad, device=x.device,
-                          dtype=torch.float32 if out_fp32 else torch.bfloat16)
+        shape = (n, cout_pad, ho, wo) if planar else (n, ho, wo, cout_pad)
+        out = torch.empty(*shape, device=x.device, dtype=torch.float32 if (out_fp32 or planar) else torch.bfloat16)
     a = _lib.Conv2dArgs()
     a.x = x.data_ptr(); a.n, a.h, a.w, a.cin = n, h, w, cin
     a.x_sn = a.x_sh = a.x_sw = 0
@@ -71,7 +73,11 @@ def conv2d(x: torch.Tensor, packed: torch.Tensor, bias: Optional[torch.Tensor], 
         a.res_sn = res.shape[3] * res.shape[2] * res.shape[1]
     a.res_shift = res_shift
     a.y = out.data_ptr(); a.y_fp32 = int(out.dtype == torch.float32)
-    a.y_sx = out.stride(2); a.y_sy = out.stride(1); a.y_sn = out.stride(0)
+    if planar:
+        a.y_sx = out.stride(3); a.y_sy = out.stride(2); a.y_sn = out.stride(0); a.y_sc = out.stride(1)
+    else:
+        a.y_sx = out.stride(2); a.y_sy = out.stride(1); a.y_sn = out.stride(0); a.y_sc = 1
+    a.epilogue = epilogue
     a.n_valid = _p(n_valid)
     a.block_n, a.stages, a.tiled = block_n, stages, int(tiled)
     check(lib.dpb200_conv2d(C.byref(a), _stream()), "dpb200_conv2d")
@@ -221,13 +227,19 @@ def avgpool(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
-def predictor_upsample(low: torch.Tensor, kc: int):
-    """low [R,S,S,Cpad] fp32 NHWC -> (coarse [R,kc,2S,2S], fine, u, v) NCHW fp32."""
-    r, s, _, cpad = low.shape
+def predictor_upsample(low: torch.Tensor, kc: int, planar: bool = False):
+    """low [R,S,S,Cpad] fp32 NHWC (or, planar=True, the phase-planar [R,2,2,Cpad,S/2,S/2] the deconv GEMM
+    writes) -> (coarse [R,kc,2S,2S], fine, u, v) NCHW fp32."""
+    if planar:
+        r, _, _, cpad, sh, _ = low.shape
+        s = 2 * sh
+    else:
+        r, s, _, cpad = low.shape
     dev = low.device
+    assert low.is_contiguous() and low.dtype == torch.float32
     outs = [torch.empty(r, c, 2 * s, 2 * s, device=dev) for c in (kc, 25, 25, 25)]
-    check(lib.dpb200_predictor_upsample(low.data_ptr(), r, s, cpad, kc, None, *[o.data_ptr() for o in outs], _stream()),
-          "dpb200_predictor_upsample")
+    check(lib.dpb200_predictor_upsample(low.data_ptr(), r, s, cpad, kc, None, *[o.data_ptr() for o in outs],
+                                        int(planar), _stream()), "dpb200_predictor_upsample")
     return outs
 
 

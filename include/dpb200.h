@@ -58,6 +58,9 @@ typedef struct dpb200_conv2d_args {
   const int32_t* n_valid;   /* optional device scalar: only the first *n_valid images are computed */
   int32_t block_n, stages;  /* 0 = automatic                                                    */
   int32_t tiled;            /* 0: A operand via im2col-mode TMA; 1: via tiled 4-D boxes         */
+  int64_t y_sc;             /* output channel stride in elements (0 or 1 = NHWC; >1 = channel-planar, fp32 only) */
+  int32_t epilogue;         /* 0 automatic; 1 direct global stores; 2 shared-memory slabs + TMA store (bf16
+                               [M,C] outputs; the residual is then prefetched by TMA too)            */
 } dpb200_conv2d_args;
 
 int dpb200_conv2d(const dpb200_conv2d_args* a, void* stream);
@@ -132,10 +135,12 @@ int dpb200_groupnorm_relu(const void* x, const float* gamma, const float* beta, 
 int dpb200_avgpool(const void* x, void* y, int32_t r, int32_t hw, int32_t c, const int32_t* n_valid, void* stream);
 
 /* interp2d (bilinear x2) of DensePoseChartPredictor.forward (densepose/modeling/predictors/chart.py:62-90).
- * low [R,S,S,cpad] fp32 NHWC (coarse[kc], fine[25], u[25], v[25]) -> four NCHW fp32 [R,C,2S,2S]. */
+ * low [R,S,S,cpad] fp32 NHWC (coarse[kc], fine[25], u[25], v[25]) -> four NCHW fp32 [R,C,2S,2S].
+ * planar != 0: low is [R,2,2,cpad,S/2,S/2] — the four ConvTranspose output phases (py,px) as channel planes,
+ * the layout dpb200_conv2d writes with y_sc > 1. */
 int dpb200_predictor_upsample(const float* low, int32_t r, int32_t s, int32_t cpad, int32_t kc,
                               const int32_t* n_valid, float* coarse, float* fine, float* u, float* v,
-                              void* stream);
+                              int32_t planar, void* stream);
 
 /* DensePoseResultExtractor (visualizer.py:10-56): per-box resize + argmax + U/V gather.
  * box_wh [D,2] = (max(int(w),1), max(int(h),1)); offsets [D+1] pixel prefix sums; labels int64 packed;

@@ -323,8 +323,9 @@ def test_avgpool_and_broadcast_gn(ops):
 
 
 # ----------------------------------------------------------------------------------------------- predictor tail + extractor
+@pytest.mark.parametrize("planar", [False, True])
 @pytest.mark.parametrize("S,kc", [(56, 2), (28, 15)])
-def test_predictor_upsample(ops, S, kc):
+def test_predictor_upsample(ops, S, kc, planar):
     g = torch.Generator().manual_seed(S)
     C = kc + 75
     cpad = (C + 15) // 16 * 16
@@ -332,7 +333,9 @@ def test_predictor_upsample(ops, S, kc):
     ref = F.interpolate(low, scale_factor=2.0, mode="bilinear", align_corners=False)   # chart.py:72-74
     lin = torch.zeros(3, S, S, cpad)
     lin[..., :C] = low.permute(0, 2, 3, 1)
-    outs = ops.predictor_upsample(lin.cuda().contiguous(), kc)
+    if planar:   # [R, py, px, c, S/2, S/2]: pixel (2*yy+py, 2*xx+px)
+        lin = lin.view(3, S // 2, 2, S // 2, 2, cpad).permute(0, 2, 4, 5, 1, 3)
+    outs = ops.predictor_upsample(lin.cuda().contiguous(), kc, planar=planar)
     torch.cuda.synchronize()
     got = torch.cat([o.cpu() for o in outs], dim=1)
     assert float((got - ref).abs().max()) < 2e-6
