@@ -44,7 +44,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                   const ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5;
+  // warp index made provably warp-uniform, so the role loops below compile to uniform-datapath code
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   // 1024-byte aligned stage buffers (SWIZZLE_128B atoms are 8 rows x 128 B)
@@ -106,8 +107,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int hw_out = p.H_out * p.W_out;
   const int m_valid = nvalid * hw_out;
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------ TMA producer
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (whole warp runs the loop
+    // with warp-uniform values; one elected lane issues the copies)
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -137,24 +139,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kx = 0; kx < p.kw; ++kx) {
           for (int cc = 0; cc < p.cin_chunks; ++cc) {
             mbar_wait(empty_bar(s), ph ^ 1u);
-            const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
-            mbar_expect_tx(full_bar(s), a_tx + b_bytes);
-            if (p.im2col)
-              tma_load_im2col_4d(a_dst, &tmA, full_bar(s), cc * 64, ix0, iy0, in0,
-                                 (uint16_t)(kx * p.dil), (uint16_t)(ky * p.dil));
-            else
-              tma_load_4d(a_dst, &tmA, full_bar(s), cc * 64, ix0 + kx * p.dil, iy0 + ky * p.dil,
-                          in0);
-            tma_load_2d(a_dst + kABytes, &tmB, full_bar(s), kcol, n_blk * p.block_n);
+            if (elect_one()) {
+              const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
+              mbar_expect_tx(full_bar(s), a_tx + b_bytes);
+              if (p.im2col)
+                tma_load_im2col_4d(a_dst, &tmA, full_bar(s), cc * 64, ix0, iy0, in0,
+                                   (uint16_t)(kx * p.dil), (uint16_t)(ky * p.dil));
+              else
+                tma_load_4d(a_dst, &tmA, full_bar(s), cc * 64, ix0 + kx * p.dil, iy0 + ky * p.dil,
+                            in0);
+              tma_load_2d(a_dst + kABytes, &tmB, full_bar(s), kcol, n_blk * p.block_n);
+            }
+            __syncwarp();
             kcol += 64;
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane)
     const uint32_t idesc = umma_idesc_bf16(128, p.block_n);
+    const uint32_t desc_lo0 = (uint32_t)(umma_desc_sw128(smem_base) & 0xffffffffu);
+    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO | version | SWIZZLE_128B
     int s = 0;
     uint32_t ph = 0;
     int as = 0;
@@ -172,17 +179,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int it = 0; it < k_iters; ++it) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
-        const uint32_t b_addr = a_addr + kABytes;
+        if (elect_one()) {
+          // descriptor low word = 16-byte-unit address | LBO: stepping a stage or a K=16 slice is an add
+          const uint32_t a_lo = desc_lo0 + (uint32_t)s * (stage_bytes >> 4);
+          const uint32_t b_lo = a_lo + (kABytes >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32),
-                    idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(d_tmem, ((uint64_t)kDescHi << 32) | (a_lo + 2u * k), ((uint64_t)kDescHi << 32) | (b_lo + 2u * k),
+                      idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));  // frees the smem slot when these MMAs retire
         }
-        umma_commit(empty_bar(s));  // frees the smem slot when these MMAs retire
+        __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+      if (elect_one()) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+      __syncwarp();
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
   } else if (kStaged && warp == 2 && lane == 0 && p.res_tma) {
