@@ -31,9 +31,42 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
-static constexpr int kThreads = 256;
+static constexpr int kThreads = 384;          // TMA / MMA / residual / store warps + 8 epilogue warps
+static constexpr int kEpiThreads = 256;
 static constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
 static constexpr int kSlabBytes = 128 * 128;  // epilogue slab: 128 rows x 64 bf16, 128B-swizzled
+
+// One thread's 32 accumulator columns of a slab row: + bias (+ residual read back from the slab) -> relu ->
+// bf16 -> four 16-byte swizzled shared stores. Adds are packed f32x2 (IEEE rn, same results as scalar adds).
+template <bool kRes>
+__device__ __forceinline__ void epi_slab_half(const uint32_t* v, const float4* bv, uint32_t srow, uint32_t sw,
+                                              int hh, bool relu) {
+#pragma unroll
+  for (int c8 = 0; c8 < 4; ++c8) {
+    const float4 b0 = bv[2 * c8], b1 = bv[2 * c8 + 1];
+    uint64_t a01 = add_f32x2(pack_f32x2(v[c8 * 8 + 0], v[c8 * 8 + 1]), pack_f32x2(__float_as_uint(b0.x), __float_as_uint(b0.y)));
+    uint64_t a23 = add_f32x2(pack_f32x2(v[c8 * 8 + 2], v[c8 * 8 + 3]), pack_f32x2(__float_as_uint(b0.z), __float_as_uint(b0.w)));
+    uint64_t a45 = add_f32x2(pack_f32x2(v[c8 * 8 + 4], v[c8 * 8 + 5]), pack_f32x2(__float_as_uint(b1.x), __float_as_uint(b1.y)));
+    uint64_t a67 = add_f32x2(pack_f32x2(v[c8 * 8 + 6], v[c8 * 8 + 7]), pack_f32x2(__float_as_uint(b1.z), __float_as_uint(b1.w)));
+    const uint32_t saddr = srow + ((((uint32_t)(hh * 4 + c8)) ^ sw) << 4);
+    if (kRes) {
+      const uint4 r = ld_shared_v4(saddr);
+      a01 = add_f32x2(a01, pack_f32x2(r.x << 16, r.x & 0xffff0000u));
+      a23 = add_f32x2(a23, pack_f32x2(r.y << 16, r.y & 0xffff0000u));
+      a45 = add_f32x2(a45, pack_f32x2(r.z << 16, r.z & 0xffff0000u));
+      a67 = add_f32x2(a67, pack_f32x2(r.w << 16, r.w & 0xffff0000u));
+    }
+    uint4 o;
+    if (relu) {
+      o.x = cvt_bf16x2_relu(a01); o.y = cvt_bf16x2_relu(a23);
+      o.z = cvt_bf16x2_relu(a45); o.w = cvt_bf16x2_relu(a67);
+    } else {
+      o.x = cvt_bf16x2(a01); o.y = cvt_bf16x2(a23);
+      o.z = cvt_bf16x2(a45); o.w = cvt_bf16x2(a67);
+    }
+    st_shared_v4(saddr, o);
+  }
+}
 
 // kStaged: bf16 NHWC outputs leave through shared-memory slabs and TMA stores (and the residual arrives by
 // TMA into the same slab), so the epilogue warps only touch TMEM and shared memory. Otherwise every
@@ -84,11 +117,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(tempty_bar(s), kEpiThreads);
     }
     for (int s = 0; s < p.nslab; ++s) {
       mbar_init(sres_bar(s), 1);
-      mbar_init(sready_bar(s), 128);
+      mbar_init(sready_bar(s), kEpiThreads);
       mbar_init(sfree_bar(s), 1);
     }
     fence_mbar_init();
@@ -244,11 +277,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_store_wait_all();
   } else if (kStaged && warp >= 4) {
     // ------------------------------------------------------------ epilogue through shared-memory slabs
+    // 8 warps: TMEM lane quarter q = warp % 4; warps 4-7 take channels 0-31 of every 64-channel slab,
+    // warps 8-11 channels 32-63. Per slab a thread does one tcgen05.ld.x32, bias / residual adds as packed
+    // f32x2, a fused relu + bf16x2 convert and four 16-byte swizzled shared stores.
     const int q = warp & 3;
+    const int hh = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const int slabs_per_tile = p.block_n >> 6;
     const uint32_t row_off = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
+    const bool has_res = p.res != nullptr;
     int as = 0, slot = 0;
     uint32_t aph = 0, sph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -256,59 +294,59 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int mt = tile / p.n_blocks;
       const int m0 = mt * 128;
       if (m0 >= m_valid) continue;
-      const int c_base = n_blk * p.block_n;
-      const __nv_bfloat16* res_ptr = nullptr;
-      if (p.res != nullptr && !p.res_tma) {      // top-down add (res_shift) or an irregular residual view
+      const int c_base = n_blk * p.block_n + hh * 32;
+      uint32_t res_off = 0;                       // element offset of this row's residual pixel (gathered mode)
+      if (has_res && !p.res_tma) {               // top-down add (res_shift) or an irregular residual view
         int m = m0 + row;
         if (m > p.N * hw_out - 1) m = p.N * hw_out - 1;
         const int on = m / hw_out;
         const int rem = m - on * hw_out;
         const int oy = rem / p.W_out, ox = rem - oy * p.W_out;
-        res_ptr = p.res + on * p.res_sn + (long long)(oy >> p.res_shift) * p.res_sy +
-                  (long long)(ox >> p.res_shift) * p.res_sx + c_base;
+        res_off = (uint32_t)(on * p.res_sn + (long long)(oy >> p.res_shift) * p.res_sy +
+                             (long long)(ox >> p.res_shift) * p.res_sx) + (uint32_t)c_base;
       }
-      mbar_wait(tfull_bar(as), aph);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.acc_stride);
+      bool acc_ready = false;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.acc_stride + hh * 32);
       for (int j = 0; j < slabs_per_tile; ++j) {
-        if (p.res_tma) mbar_wait(sres_bar(slot), sph);
-        else mbar_wait(sfree_bar(slot), sph ^ 1u);
-        const uint32_t srow = slab_base + (uint32_t)slot * kSlabBytes + row_off;
+        const uint32_t slab = slab_base + (uint32_t)slot * kSlabBytes;
+        float4 bv[8];
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + c_base + j * 64);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          tmem_ld32(t_addr + (uint32_t)(j * 64 + h * 32), v);
-          tmem_ld_wait();
+          for (int i = 0; i < 8; ++i) bv[i] = __ldg(b4 + i);
+        } else {
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            float f[8];
+          for (int i = 0; i < 8; ++i) bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (p.res_tma) {
+          mbar_wait(sres_bar(slot), sph);
+        } else {
+          mbar_wait(sfree_bar(slot), sph ^ 1u);
+          if (has_res) {
+            // gathered residual: the warp copies its 32 rows x 64 B into the slab with coalesced 64-byte
+            // row segments (4 lanes per row, 8 rows per request), then every thread reads its own row back
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[c8 * 8 + i]);
-            const int ch = j * 64 + h * 32 + c8 * 8;       // channel offset inside the N block
-            if (p.bias != nullptr) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + c_base + ch);
-              const float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1);
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            for (int i = 0; i < 4; ++i) {
+              const int r = 8 * i + (lane >> 2);
+              const uint32_t off = __shfl_sync(0xffffffffu, res_off, r);
+              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.res + off + j * 64) + (lane & 3));
+              const uint32_t rr = (uint32_t)(q * 32 + r);
+              st_shared_v4(slab + rr * 128u + ((((uint32_t)(hh * 4 + (lane & 3))) ^ (rr & 7u)) << 4), rv);
             }
-            const uint32_t saddr = srow + ((((uint32_t)(h * 4 + c8)) ^ sw) << 4);
-            if (p.res_tma || res_ptr != nullptr) {
-              uint4 r;
-              if (p.res_tma) r = ld_shared_v4(saddr);
-              else r = __ldg(reinterpret_cast<const uint4*>(res_ptr + ch));
-              f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x); f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
-              f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z); f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
-            }
-            uint4 o;
-            o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-            o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-            st_shared_v4(saddr, o);
+            __syncwarp();
           }
         }
+        if (!acc_ready) {
+          mbar_wait(tfull_bar(as), aph);
+          tc_fence_after();
+          acc_ready = true;
+        }
+        uint32_t v[32];
+        tmem_ld32(t_addr + (uint32_t)(j * 64), v);
+        tmem_ld_wait();
+        const uint32_t srow = slab + row_off;
+        if (has_res) epi_slab_half<true>(v, bv, srow, sw, hh, p.relu != 0);
+        else epi_slab_half<false>(v, bv, srow, sw, hh, p.relu != 0);
         fence_proxy_async();            // generic-proxy slab writes -> visible to the TMA store
         mbar_arrive(sready_bar(slot));
         if (++slot == p.nslab) { slot = 0; sph ^= 1u; }
@@ -319,7 +357,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (!kStaged && warp >= 4) {
     // ------------------------------------------------------------ epilogue, direct global stores
+    // 8 warps: lane quarter q = warp % 4; the two warps of a quarter alternate 16-column chunks
     const int q = warp & 3;
+    const int hh = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const int rows_in_tile = p.im2col ? 128 : p.tw * p.th * p.tn;
     const int rx = p.im2col ? 0 : row % p.tw;
@@ -360,7 +400,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.acc_stride);
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      for (int c0 = hh * 16; c0 < p.block_n; c0 += 32) {
         uint32_t v[16];
         __syncwarp();
         tmem_ld16(t_addr + (uint32_t)c0, v);

@@ -205,6 +205,29 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
+// Packed fp32 pairs (sm_100 add.f32x2: two IEEE round-to-nearest adds per instruction).
+__device__ __forceinline__ uint64_t pack_f32x2(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// (lo, hi) fp32 pair -> packed bf16x2 (lo in the low half), round to nearest even; _relu clamps at 0 first.
+__device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {
+  uint32_t d;
+  asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tcvt.rn.bf16x2.f32 %0, hi, lo;\n\t}\n" : "=r"(d) : "l"(v));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2_relu(uint64_t v) {
+  uint32_t d;
+  asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tcvt.rn.relu.bf16x2.f32 %0, hi, lo;\n\t}\n" : "=r"(d) : "l"(v));
+  return d;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
