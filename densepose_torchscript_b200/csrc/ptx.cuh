@@ -216,6 +216,13 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// NOTE: ptxas 12.9 contracts mul.rn.f32x2 followed by add.rn.f32x2 into FFMA2 even though both carry explicit
+// rounding modifiers; only use this where no dependent add follows (or where a fused result is acceptable).
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 // (lo, hi) fp32 pair -> packed bf16x2 (lo in the low half), round to nearest even; _relu clamps at 0 first.
 __device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {
   uint32_t d;

@@ -20,27 +20,45 @@ namespace dpb {
 
 
 // ------------------------------------------------------------------------------------ ROIAlign
-struct Tap {
+// torchvision bilinear pre-calc for one sample coordinate (aligned=False): source rows/cols lo, hi and the
+// weights l (towards hi) and h = 1 - l. lo < 0 marks a sample outside [-1, size] (contributes nothing).
+struct __align__(16) Tap {
   int lo, hi;
   float l, h;
-  bool dead;
 };
-// torchvision bilinear pre-calc for one coordinate (aligned=False)
 __device__ __forceinline__ Tap make_tap(float v, int size) {
   Tap t;
-  t.dead = (v < -1.0f) || (v > (float)size);
+  const bool dead = (v < -1.0f) || (v > (float)size);
   if (v <= 0.f) v = 0.f;
   int lo = (int)v;
   int hi;
   if (lo >= size - 1) { hi = lo = size - 1; v = (float)lo; }
   else hi = lo + 1;
-  t.lo = lo; t.hi = hi;
+  t.lo = dead ? -1 : lo; t.hi = hi;
   t.l = __fsub_rn(v, (float)lo);
   t.h = __fsub_rn(1.f, t.l);
   return t;
 }
 
+// acc += ((w1*v1 + w2*v2) + w3*v3) + w4*v4 for one bf16 pair of each of the four taps; every product and
+// sum individually rounded (torchvision's CPU kernel has no FMA contraction). Products are scalar mul.rn
+// (never contracted); the sums are packed add.rn.f32x2. (ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into
+// FFMA2 despite the explicit rounding modifiers, so the products must not be packed.)
+__device__ __forceinline__ uint64_t prod2(float w, uint32_t q) {
+  return pack_f32x2(__float_as_uint(__fmul_rn(w, __uint_as_float(q << 16))),
+                    __float_as_uint(__fmul_rn(w, __uint_as_float(q & 0xffff0000u))));
+}
+__device__ __forceinline__ uint64_t tap_accum(uint64_t acc, uint32_t q1, uint32_t q2, uint32_t q3, uint32_t q4,
+                                              float w1, float w2, float w3, float w4) {
+  const uint64_t sum = add_f32x2(add_f32x2(add_f32x2(prod2(w1, q1), prod2(w2, q2)), prod2(w3, q3)), prod2(w4, q4));
+  return add_f32x2(acc, sum);
+}
+
+// One block per ROI. The 2P sample coordinates per axis are resolved once into shared-memory tap tables;
+// then a group of C/8 threads (16 bytes of channels each) walks the bins: 16 independent 16-byte loads in
+// flight per thread, packed f32x2 arithmetic, one 16-byte store.
 __global__ void __launch_bounds__(256) roi_align_kernel(RoiAlignArgs a) {
+  __shared__ Tap s_ty[64], s_tx[64];
   const int r = blockIdx.x;
   if (a.n_rois != nullptr && r >= *a.n_rois) return;
   const float* roi = a.rois + (long long)r * 5;
@@ -61,63 +79,62 @@ __global__ void __launch_bounds__(256) roi_align_kernel(RoiAlignArgs a) {
   const int C8 = a.C / 8;
   const uint4* feat = reinterpret_cast<const uint4*>(a.feat[lvl]) + (long long)b * H * W * C8;
   const int P = a.P;
-  const float fx0 = __fmul_rn(x1, scale), fy0 = __fmul_rn(y1, scale);
-  const float rw = fmaxf(__fsub_rn(__fmul_rn(x2, scale), fx0), 1.f);
-  const float rh = fmaxf(__fsub_rn(__fmul_rn(y2, scale), fy0), 1.f);
-  const float bw = __fdiv_rn(rw, (float)P), bh = __fdiv_rn(rh, (float)P);
+  {
+    const float fx0 = __fmul_rn(x1, scale), fy0 = __fmul_rn(y1, scale);
+    const float rw = fmaxf(__fsub_rn(__fmul_rn(x2, scale), fx0), 1.f);
+    const float rh = fmaxf(__fsub_rn(__fmul_rn(y2, scale), fy0), 1.f);
+    const float bw = __fdiv_rn(rw, (float)P), bh = __fdiv_rn(rh, (float)P);
+    const int t = threadIdx.x;
+    if (t < 2 * P) {            // y samples: index 2*ph + iy
+      const int ph = t >> 1, iy = t & 1;
+      const float yy = __fadd_rn(__fadd_rn(fy0, __fmul_rn((float)ph, bh)),
+                                 __fdiv_rn(__fmul_rn((float)iy + 0.5f, bh), 2.f));
+      s_ty[t] = make_tap(yy, H);
+    } else if (t >= 128 && t < 128 + 2 * P) {
+      const int u = t - 128, pw = u >> 1, ix = u & 1;
+      const float xx = __fadd_rn(__fadd_rn(fx0, __fmul_rn((float)pw, bw)),
+                                 __fdiv_rn(__fmul_rn((float)ix + 0.5f, bw), 2.f));
+      s_tx[u] = make_tap(xx, W);
+    }
+  }
+  __syncthreads();
 
   const int chunk = threadIdx.x % C8;
   const int group = threadIdx.x / C8, groups = blockDim.x / C8;
+  const uint4* fc = feat + chunk;
   for (int bin = group; bin < P * P; bin += groups) {
     const int ph = bin / P, pw = bin - ph * P;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;    // four (+0, +0) pairs = 8 channels
 #pragma unroll
     for (int iy = 0; iy < 2; ++iy) {
-      const float yy = __fadd_rn(__fadd_rn(fy0, __fmul_rn((float)ph, bh)),
-                                 __fdiv_rn(__fmul_rn((float)iy + 0.5f, bh), 2.f));
-      const Tap ty = make_tap(yy, H);
+      const Tap ty = s_ty[2 * ph + iy];
 #pragma unroll
       for (int ix = 0; ix < 2; ++ix) {
-        const float xx = __fadd_rn(__fadd_rn(fx0, __fmul_rn((float)pw, bw)),
-                                   __fdiv_rn(__fmul_rn((float)ix + 0.5f, bw), 2.f));
-        const Tap tx = make_tap(xx, W);
-        if (ty.dead || tx.dead) continue;
+        const Tap tx = s_tx[2 * pw + ix];
+        if (ty.lo < 0 || tx.lo < 0) continue;
         const float w1 = __fmul_rn(ty.h, tx.h), w2 = __fmul_rn(ty.h, tx.l);
         const float w3 = __fmul_rn(ty.l, tx.h), w4 = __fmul_rn(ty.l, tx.l);
-        float v1[8], v2[8], v3[8], v4[8];
-        const uint4 q1 = __ldg(feat + ((long long)ty.lo * W + tx.lo) * C8 + chunk);
-        const uint4 q2 = __ldg(feat + ((long long)ty.lo * W + tx.hi) * C8 + chunk);
-        const uint4 q3 = __ldg(feat + ((long long)ty.hi * W + tx.lo) * C8 + chunk);
-        const uint4 q4 = __ldg(feat + ((long long)ty.hi * W + tx.hi) * C8 + chunk);
-        v1[0] = bf16_lo(q1.x); v1[1] = bf16_hi(q1.x); v1[2] = bf16_lo(q1.y); v1[3] = bf16_hi(q1.y);
-        v1[4] = bf16_lo(q1.z); v1[5] = bf16_hi(q1.z); v1[6] = bf16_lo(q1.w); v1[7] = bf16_hi(q1.w);
-        v2[0] = bf16_lo(q2.x); v2[1] = bf16_hi(q2.x); v2[2] = bf16_lo(q2.y); v2[3] = bf16_hi(q2.y);
-        v2[4] = bf16_lo(q2.z); v2[5] = bf16_hi(q2.z); v2[6] = bf16_lo(q2.w); v2[7] = bf16_hi(q2.w);
-        v3[0] = bf16_lo(q3.x); v3[1] = bf16_hi(q3.x); v3[2] = bf16_lo(q3.y); v3[3] = bf16_hi(q3.y);
-        v3[4] = bf16_lo(q3.z); v3[5] = bf16_hi(q3.z); v3[6] = bf16_lo(q3.w); v3[7] = bf16_hi(q3.w);
-        v4[0] = bf16_lo(q4.x); v4[1] = bf16_hi(q4.x); v4[2] = bf16_lo(q4.y); v4[3] = bf16_hi(q4.y);
-        v4[4] = bf16_lo(q4.z); v4[5] = bf16_hi(q4.z); v4[6] = bf16_lo(q4.w); v4[7] = bf16_hi(q4.w);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          // output_val += w1*v1 + w2*v2 + w3*v3 + w4*v4, each product and sum rounded (no FMA)
-          const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1[i]), __fmul_rn(w2, v2[i])),
-                                              __fmul_rn(w3, v3[i])),
-                                    __fmul_rn(w4, v4[i]));
-          acc[i] = __fadd_rn(acc[i], s);
-        }
+        const uint4 q1 = __ldg(fc + (ty.lo * W + tx.lo) * C8);
+        const uint4 q2 = __ldg(fc + (ty.lo * W + tx.hi) * C8);
+        const uint4 q3 = __ldg(fc + (ty.hi * W + tx.lo) * C8);
+        const uint4 q4 = __ldg(fc + (ty.hi * W + tx.hi) * C8);
+        acc0 = tap_accum(acc0, q1.x, q2.x, q3.x, q4.x, w1, w2, w3, w4);
+        acc1 = tap_accum(acc1, q1.y, q2.y, q3.y, q4.y, w1, w2, w3, w4);
+        acc2 = tap_accum(acc2, q1.z, q2.z, q3.z, q4.z, w1, w2, w3, w4);
+        acc3 = tap_accum(acc3, q1.w, q2.w, q3.w, q4.w, w1, w2, w3, w4);
       }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = __fdiv_rn(acc[i], 4.f);
+    // / count (= 4): a power of two, so the multiply is the exactly rounded quotient as well
+    const uint64_t qq = pack_f32x2(__float_as_uint(0.25f), __float_as_uint(0.25f));
+    acc0 = mul_f32x2(acc0, qq); acc1 = mul_f32x2(acc1, qq); acc2 = mul_f32x2(acc2, qq); acc3 = mul_f32x2(acc3, qq);   // no add follows
     const long long o = ((long long)r * P * P + bin) * a.C + chunk * 8;
     if (a.out_fp32) {
-      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + o);
-      dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<float*>(a.out) + o);
+      dst[0] = make_uint4((uint32_t)acc0, (uint32_t)(acc0 >> 32), (uint32_t)acc1, (uint32_t)(acc1 >> 32));
+      dst[1] = make_uint4((uint32_t)acc2, (uint32_t)(acc2 >> 32), (uint32_t)acc3, (uint32_t)(acc3 >> 32));
     } else {
       uint4 v;
-      v.x = pack_bf16(acc[0], acc[1]); v.y = pack_bf16(acc[2], acc[3]);
-      v.z = pack_bf16(acc[4], acc[5]); v.w = pack_bf16(acc[6], acc[7]);
+      v.x = cvt_bf16x2(acc0); v.y = cvt_bf16x2(acc1); v.z = cvt_bf16x2(acc2); v.w = cvt_bf16x2(acc3);
       *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.out) + o) = v;
     }
   }
@@ -125,6 +142,7 @@ __global__ void __launch_bounds__(256) roi_align_kernel(RoiAlignArgs a) {
 
 int launch_roi_align(const RoiAlignArgs& a, cudaStream_t s) {
   if (a.C % 8 || 256 % (a.C / 8)) { set_error("roi_align: C/8 must divide 256"); return -1; }
+  if (a.P > 32) { set_error("roi_align: pooler resolution %d > 32", a.P); return -1; }
   if (a.R == 0) return 0;
   roi_align_kernel<<<a.R, 256, 0, s>>>(a);
   DPB_CHECK_LAUNCH("roi_align");
