@@ -132,6 +132,21 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback"
 
 
+def ncu_conv_traffic_gb():
+    """DRAM read+write bytes of the conv launches of one step, from the committed ncu capture of this workload."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r01_ncu_step_sections.csv")
+    if not os.path.exists(p):
+        return None, None
+    rows = list(csv.reader(open(p)))
+    h = rows[0]
+    ir, iw, io = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("op")
+    ur, uw = rows[1][ir], rows[1][iw]
+    scale = {"Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0, "byte": 1e-9}
+    tot = sum(float(r[ir]) * scale[ur] + float(r[iw]) * scale[uw] for r in rows[2:] if r[io].startswith("conv:"))
+    return tot, "profiles/r01_ncu_step_sections.csv"
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def cpu_reference_rate(height, width, steps, warmup, config=CONFIG, max_seconds=120.0):
     """images/s of the reference's CPU path (oracle port, fp32, mode='ref') on this host."""
@@ -291,6 +306,8 @@ def run_ours(a):
             json.dump([{"i": i, "name": n, "ms": ms, "padded_gflop": fl / 1e9} for i, ((n, fl), ms) in enumerate(zip(info, prof))], f, indent=0)
     conv_ms = sum(ms for (n, _), ms in zip(info, prof) if n.startswith("conv:"))
     total_ms = sum(prof)
+    op_bytes = sess.op_bytes()
+    conv_gb = sum(b for (n, _), b in zip(info, op_bytes) if n.startswith("conv:")) / 1e9
 
     # max over ranks
     t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
@@ -330,6 +347,19 @@ def run_ours(a):
                          "step_tflops": gflop_step / (ms_dev / a.steps)},
             "top_launches_ms": [[round(ms, 4), n] for ms, n in top],
         }
+        # measured DRAM traffic of the conv launches of one step (ncu capture committed under profiles/)
+        traffic, traffic_src = ncu_conv_traffic_gb()
+        line["roofline"].update({"traffic": traffic, "traffic_unit": "GB of DRAM read+write per step over the kernel's launches",
+                                 "traffic_source": traffic_src, "algorithmic_gb_per_step": conv_gb})
+        # the memory-bound stage kernels against the measured HBM copy bandwidth
+        agg = {}
+        for (n, _), ms, by in zip(info, prof, op_bytes):
+            if not n.startswith("conv:") and by > 0:
+                a_ = agg.setdefault(n, [0.0, 0.0, 0])
+                a_[0] += ms; a_[1] += by; a_[2] += 1
+        line["hbm_kernels"] = [{"kernel": n, "launches": c, "ms": round(ms, 4), "algorithmic_gb": round(by / 1e9, 4),
+                                "achieved_gbs": round(by / 1e6 / ms, 1), "frac_of_measured_hbm": round(by / 1e6 / ms / peak_hbm, 3)}
+                               for n, (ms, by, c) in sorted(agg.items(), key=lambda t: -t[1][0])]
         if lat is not None:
             line["latency_batch1"] = lat
         if world == 1 and not a.no_cpu_baseline:

@@ -138,6 +138,7 @@ _proto("dpb200_session_set_graph", C.c_int, [vp, i32])
 _proto("dpb200_session_launch_count", C.c_int, [vp])
 _proto("dpb200_session_flops", C.c_double, [vp])
 _proto("dpb200_session_op_info", C.c_int, [vp, i32, C.c_char_p, i32, C.POINTER(C.c_double)])
+_proto("dpb200_session_op_bytes", C.c_int, [vp, i32, C.POINTER(C.c_double)])
 _proto("dpb200_session_profile", C.c_int, [vp, C.POINTER(ForwardIO), vp, C.POINTER(f32), i32])
 _proto("dpb200_session_geometry", None, [vp, C.POINTER(i32 * 4)])
 _proto("dpb200_session_tap", C.c_int, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(i64 * 4), C.POINTER(i32)])
@@ -148,7 +149,7 @@ EXPORTS = [
     "dpb200_nms_sorted", "dpb200_roi_align", "dpb200_box_predict", "dpb200_groupnorm_relu", "dpb200_avgpool",
     "dpb200_predictor_upsample", "dpb200_dp_resample", "dpb200_model_create", "dpb200_model_destroy",
     "dpb200_session_workspace_bytes", "dpb200_session_create", "dpb200_session_destroy", "dpb200_session_run", "dpb200_session_set_graph",
-    "dpb200_session_launch_count", "dpb200_session_flops", "dpb200_session_op_info", "dpb200_session_profile", "dpb200_session_geometry", "dpb200_session_tap",
+    "dpb200_session_launch_count", "dpb200_session_flops", "dpb200_session_op_info", "dpb200_session_op_bytes", "dpb200_session_profile", "dpb200_session_geometry", "dpb200_session_tap",
 ]
 
 

@@ -307,6 +307,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       bool acc_ready = false;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.acc_stride + hh * 32);
+      // gathered residual: rows r = 8*i + lane/4 (i = 0..3), 16-byte chunk lane%4 of this warp's 64-byte half.
+      // The loads for slab j+1 are issued before slab j is processed, so only the first slab of a tile
+      // exposes their latency (and that one overlaps the wait for the accumulator).
+      const bool gather = has_res && !p.res_tma;
+      uint32_t goff[4];
+      uint4 gv[4];
+      if (gather) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          goff[i] = __shfl_sync(0xffffffffu, res_off, 8 * i + (lane >> 2));
+          gv[i] = __ldg(reinterpret_cast<const uint4*>(p.res + goff[i]) + (lane & 3));
+        }
+      }
       for (int j = 0; j < slabs_per_tile; ++j) {
         const uint32_t slab = slab_base + (uint32_t)slot * kSlabBytes;
         float4 bv[8];
@@ -322,18 +335,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(sres_bar(slot), sph);
         } else {
           mbar_wait(sfree_bar(slot), sph ^ 1u);
-          if (has_res) {
-            // gathered residual: the warp copies its 32 rows x 64 B into the slab with coalesced 64-byte
-            // row segments (4 lanes per row, 8 rows per request), then every thread reads its own row back
+          if (gather) {
+            // the warp copies its 32 rows x 64 B into the slab with coalesced 64-byte row segments (4 lanes
+            // per row, 8 rows per request); every thread then reads its own row back like a TMA residual
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int r = 8 * i + (lane >> 2);
-              const uint32_t off = __shfl_sync(0xffffffffu, res_off, r);
-              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.res + off + j * 64) + (lane & 3));
-              const uint32_t rr = (uint32_t)(q * 32 + r);
-              st_shared_v4(slab + rr * 128u + ((((uint32_t)(hh * 4 + (lane & 3))) ^ (rr & 7u)) << 4), rv);
+              const uint32_t rr = (uint32_t)(q * 32 + 8 * i + (lane >> 2));
+              st_shared_v4(slab + rr * 128u + ((((uint32_t)(hh * 4 + (lane & 3))) ^ (rr & 7u)) << 4), gv[i]);
             }
             __syncwarp();
+            if (j + 1 < slabs_per_tile) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                gv[i] = __ldg(reinterpret_cast<const uint4*>(p.res + goff[i] + (j + 1) * 64) + (lane & 3));
+            }
           }
         }
         if (!acc_ready) {

@@ -146,75 +146,98 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return o;
 }
 
-// acc += bilinear sample of the half-resolution tensor `x` ([.., h, w, C8]) at output pixel (oy, ox)
+// acc += bilinear sample of the half-resolution tensor `x` ([.., h, w, C8]) at output pixel (oy, ox);
+// acc is four packed (lo, hi) fp32 pairs = 8 channels, all arithmetic two channels per instruction
+__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t q) { return pack_f32x2(q << 16, q & 0xffff0000u); }
+__device__ __forceinline__ uint64_t lerp4(uint32_t q00, uint32_t q01, uint32_t q10, uint32_t q11, uint64_t HX,
+                                          uint64_t LX, uint64_t HY, uint64_t LY) {
+  const uint64_t top = fma_f32x2(LX, bf16x2_to_f32x2(q01), mul_f32x2(HX, bf16x2_to_f32x2(q00)));
+  const uint64_t bot = fma_f32x2(LX, bf16x2_to_f32x2(q11), mul_f32x2(HX, bf16x2_to_f32x2(q10)));
+  return fma_f32x2(LY, bot, mul_f32x2(HY, top));
+}
 __device__ __forceinline__ void add_up2(const uint4* __restrict__ x, int b, int h, int w, int C8, int c,
-                                        int oy, int ox, float* acc) {
+                                        int oy, int ox, uint64_t* acc) {
   int y0, y1, x0, x1;
   float ly, lx;
   up2_index(oy, h, y0, y1, ly);
   up2_index(ox, w, x0, x1, lx);
   const uint4* base = x + (long long)b * h * w * C8 + c;
-  float v00[8], v01[8], v10[8], v11[8];
-  unpack8(__ldg(base + ((long long)y0 * w + x0) * C8), v00);
-  unpack8(__ldg(base + ((long long)y0 * w + x1) * C8), v01);
-  unpack8(__ldg(base + ((long long)y1 * w + x0) * C8), v10);
-  unpack8(__ldg(base + ((long long)y1 * w + x1) * C8), v11);
+  const uint4 v00 = __ldg(base + ((long long)y0 * w + x0) * C8);
+  const uint4 v01 = __ldg(base + ((long long)y0 * w + x1) * C8);
+  const uint4 v10 = __ldg(base + ((long long)y1 * w + x0) * C8);
+  const uint4 v11 = __ldg(base + ((long long)y1 * w + x1) * C8);
   const float hy = 1.f - ly, hx = 1.f - lx;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    acc[i] += hy * (hx * v00[i] + lx * v01[i]) + ly * (hx * v10[i] + lx * v11[i]);
+  const uint64_t HX = pack_f32x2(__float_as_uint(hx), __float_as_uint(hx)), LX = pack_f32x2(__float_as_uint(lx), __float_as_uint(lx));
+  const uint64_t HY = pack_f32x2(__float_as_uint(hy), __float_as_uint(hy)), LY = pack_f32x2(__float_as_uint(ly), __float_as_uint(ly));
+  acc[0] = add_f32x2(acc[0], lerp4(v00.x, v01.x, v10.x, v11.x, HX, LX, HY, LY));
+  acc[1] = add_f32x2(acc[1], lerp4(v00.y, v01.y, v10.y, v11.y, HX, LX, HY, LY));
+  acc[2] = add_f32x2(acc[2], lerp4(v00.z, v01.z, v10.z, v11.z, HX, LX, HY, LY));
+  acc[3] = add_f32x2(acc[3], lerp4(v00.w, v01.w, v10.w, v11.w, HX, LX, HY, LY));
+}
+__device__ __forceinline__ uint4 pack8_f32x2(const uint64_t* acc) {
+  uint4 o;
+  o.x = cvt_bf16x2(acc[0]); o.y = cvt_bf16x2(acc[1]); o.z = cvt_bf16x2(acc[2]); o.w = cvt_bf16x2(acc[3]);
+  return o;
 }
 
-__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W,
-                                  int C8) {
+// Both kernels below walk the output in 8x8-pixel tiles (one CTA per tile, one warp per pixel and 16-byte
+// channel chunk per lane when C = 256), so the 5x5 half-resolution pixels a tile samples are fetched from L2
+// once and then hit in L1 instead of being re-read by CTAs that sit a full image row apart.
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W, int C8) {
   const int Ho = 2 * H, Wo = 2 * W;
-  const long long total = (long long)B * Ho * Wo * C8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C8);
-    const int ox = (int)((i / C8) % Wo);
-    const int oy = (int)((i / ((long long)C8 * Wo)) % Ho);
-    const int b = (int)(i / ((long long)C8 * Wo * Ho));
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int tiles_x = (Wo + 7) / 8, tiles_y = (Ho + 7) / 8;
+  const int b = blockIdx.x / (tiles_x * tiles_y);
+  const int t = blockIdx.x - b * tiles_x * tiles_y;
+  const int ty0 = (t / tiles_x) * 8, tx0 = (t % tiles_x) * 8;
+  for (int item = threadIdx.x; item < 64 * C8; item += blockDim.x) {
+    const int c = item % C8, pix = item / C8;
+    const int oy = ty0 + (pix >> 3), ox = tx0 + (pix & 7);
+    if (oy >= Ho || ox >= Wo) continue;
+    uint64_t acc[4] = {0, 0, 0, 0};
     add_up2(x, b, H, W, C8, c, oy, ox, acc);
-    y[i] = pack8(acc);
+    y[(((long long)b * Ho + oy) * Wo + ox) * C8 + c] = pack8_f32x2(acc);
   }
 }
 
 int launch_upsample2x(const bf16* x, bf16* y, int B, int H, int W, int C, cudaStream_t s) {
   if (C % 8) { set_error("upsample2x: C %% 8 != 0"); return -1; }
-  const long long total = (long long)B * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x),
-                                                        reinterpret_cast<uint4*>(y), B, H, W, C / 8);
+  const long long blocks = (long long)B * ((2 * H + 7) / 8) * ((2 * W + 7) / 8);
+  if (blocks > 0x7fffffffLL) { set_error("upsample2x: too large"); return -1; }
+  upsample2x_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(x),
+                                                    reinterpret_cast<uint4*>(y), B, H, W, C / 8);
   DPB_CHECK_LAUNCH("upsample2x");
   return 0;
 }
 
-__global__ void decoder_merge_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b3,
-                                     const uint4* __restrict__ b4, const uint4* __restrict__ b5,
-                                     uint4* __restrict__ out, int B, int H, int W, int C8) {
-  const long long total = (long long)B * H * W * C8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C8);
-    const int ox = (int)((i / C8) % W);
-    const int oy = (int)((i / ((long long)C8 * W)) % H);
-    const int b = (int)(i / ((long long)C8 * W * H));
-    float acc[8];
-    unpack8(__ldg(a + i), acc);
+__global__ void __launch_bounds__(256)
+decoder_merge_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b3, const uint4* __restrict__ b4,
+                     const uint4* __restrict__ b5, uint4* __restrict__ out, int B, int H, int W, int C8) {
+  const int tiles_x = (W + 7) / 8, tiles_y = (H + 7) / 8;
+  const int b = blockIdx.x / (tiles_x * tiles_y);
+  const int t = blockIdx.x - b * tiles_x * tiles_y;
+  const int ty0 = (t / tiles_x) * 8, tx0 = (t % tiles_x) * 8;
+  for (int item = threadIdx.x; item < 64 * C8; item += blockDim.x) {
+    const int c = item % C8, pix = item / C8;
+    const int oy = ty0 + (pix >> 3), ox = tx0 + (pix & 7);
+    if (oy >= H || ox >= W) continue;
+    const long long i = (((long long)b * H + oy) * W + ox) * C8 + c;
+    const uint4 a0 = __ldg(a + i);
+    uint64_t acc[4] = {bf16x2_to_f32x2(a0.x), bf16x2_to_f32x2(a0.y), bf16x2_to_f32x2(a0.z), bf16x2_to_f32x2(a0.w)};
     // reference order: ((p2 + up(p3)) + up(p4)) + up(p5)   (roi_head.py:73-77)
     add_up2(b3, b, H / 2, W / 2, C8, c, oy, ox, acc);
     add_up2(b4, b, H / 2, W / 2, C8, c, oy, ox, acc);
     add_up2(b5, b, H / 2, W / 2, C8, c, oy, ox, acc);
-    out[i] = pack8(acc);
+    out[i] = pack8_f32x2(acc);
   }
 }
 
 int launch_decoder_merge(const bf16* a, const bf16* b, const bf16* c, const bf16* d, bf16* out, int B,
                          int H, int W, int C, cudaStream_t s) {
   if (C % 8 || H % 2 || W % 2) { set_error("decoder_merge: bad shape"); return -1; }
-  const long long total = (long long)B * H * W * (C / 8);
-  decoder_merge_kernel<<<grid_for(total, 256), 256, 0, s>>>(
+  const long long blocks = (long long)B * ((H + 7) / 8) * ((W + 7) / 8);
+  if (blocks > 0x7fffffffLL) { set_error("decoder_merge: too large"); return -1; }
+  decoder_merge_kernel<<<(unsigned)blocks, 256, 0, s>>>(
       reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
       reinterpret_cast<const uint4*>(c), reinterpret_cast<const uint4*>(d),
       reinterpret_cast<uint4*>(out), B, H, W, C / 8);

@@ -44,6 +44,7 @@ struct dpb200_session {
   std::vector<std::function<int(cudaStream_t)>> ops;
   std::vector<std::string> op_names;     // "conv:<weight name>" or the stage kernel's name
   std::vector<double> op_flops;          // padded-shape 2*MAC at full capacity (conv ops), else 0
+  std::vector<double> op_bytes;          // algorithmic HBM bytes at full capacity: every operand read once, outputs written once
   std::vector<ConvPlan*> plans;
   std::map<std::string, TensorInfo> taps;
   double flops = 0;
@@ -148,6 +149,15 @@ struct Builder {
     s->flops += fl;
     s->op_names.push_back("conv:" + wname);
     s->op_flops.push_back(fl);
+    {
+      // input pixels a 1x1 strided conv never touches are not counted; weights and bias once
+      const double in_px = (d.kh == 1 && d.kw == 1) ? (double)x.N * d.H_out * d.W_out : (double)x.N * x.H * x.W;
+      const double out_px = (double)x.N * d.H_out * d.W_out;
+      double by = in_px * x.C * 2.0 + out_px * w->cout_pad * (y.fp32 ? 4.0 : 2.0) +
+                  (double)w->cout_pad * d.kh * d.kw * w->cin_pad * 2.0 + (d.bias ? w->cout_pad * 4.0 : 0.0);
+      if (o.res) by += (o.res_shift ? out_px / 4.0 : out_px) * w->cout_pad * 2.0;
+      s->op_bytes.push_back(by);
+    }
     if (s->dry) { s->ops.push_back([](cudaStream_t) { return 0; }); return; }
     ConvPlan* plan = new ConvPlan();
     int r = conv_plan_build(plan, d, m->num_sms);
@@ -155,10 +165,11 @@ struct Builder {
     s->plans.push_back(plan);
     s->ops.push_back([plan](cudaStream_t st) { return conv_plan_launch(*plan, st); });
   }
-  void op(std::function<int(cudaStream_t)> f, const char* name = "stage") {
+  void op(std::function<int(cudaStream_t)> f, const char* name = "stage", double bytes = 0.0) {
     if (fail) return;
     s->op_names.push_back(name);
     s->op_flops.push_back(0.0);
+    s->op_bytes.push_back(bytes);
     if (s->dry) { s->ops.push_back([](cudaStream_t) { return 0; }); return; }
     s->ops.push_back(std::move(f));
   }
@@ -207,7 +218,7 @@ int build_plan(dpb200_session* s) {
       p.src = ss->io->images;
       p.flip_rgb = (ss->m->cfg.input_rgb && ss->io->bgr) ? 1 : 0;   // defaults.py:82-83
       return launch_preprocess(p, st);
-    }, "preprocess");
+    }, "preprocess", (double)B * s->H0 * s->W0 * 3 * (s->src_u8 ? 1 : 4) + (double)B * Hp * s->Wx * 8);
   }
   // ---- a3 stem: 7x7/2 conv as 7 row taps over a 16-pixel (64-element) sliding window
   T4 stem = b.act(B, Hp / 2, Wp / 2, 64);
@@ -221,7 +232,7 @@ int build_plan(dpb200_session* s) {
   T4 pool = b.act(B, Hp / 4, Wp / 4, 64);
   b.op([=](cudaStream_t st) {
     return launch_maxpool3x3s2((const bf16*)stem.p, (bf16*)pool.p, B, stem.H, stem.W, 64, st);
-  }, "maxpool3x3s2");
+  }, "maxpool3x3s2", (double)stem.elems() * 2 + (double)pool.elems() * 2);
   b.tap("stem_pool", pool);
 
   // ---- a4 res2..res5
@@ -324,7 +335,8 @@ int build_plan(dpb200_session* s) {
     RoiAlignArgs a{};
     for (int l = 0; l < 4; ++l) { a.feat[l] = (const bf16*)pf[l].p; a.H[l] = pf[l].H; a.W[l] = pf[l].W; a.scale[l] = 1.0f / (float)(4 << l); }
     a.n_levels = 4; a.C = 256; a.rois = rois_box; a.n_rois = nullptr; a.R = B * R; a.P = 7; a.out = box_pooled.p; a.out_fp32 = 0;
-    b.op([a](cudaStream_t st) { return launch_roi_align(a, st); }, "roi_align_box");
+    b.op([a](cudaStream_t st) { return launch_roi_align(a, st); }, "roi_align_box",
+         (double)(pf[0].elems() + pf[1].elems() + pf[2].elems() + pf[3].elems()) * 2 + (double)box_pooled.elems() * 2);
   }
   b.tap("box_pooled", box_pooled);
   T4 fc_in = box_pooled; fc_in.H = 1; fc_in.W = 1; fc_in.C = 7 * 7 * 256;
@@ -379,7 +391,8 @@ int build_plan(dpb200_session* s) {
         b.conv("roi_heads.decoder.p" + std::to_string(l + 2) + "." + std::to_string(2 * kk), x, y, o);
         if (kk != l - 1) {
           T4 up = b.act(B, y.H * 2, y.W * 2, 256);
-          b.op([=](cudaStream_t st) { return launch_upsample2x((const bf16*)y.p, (bf16*)up.p, B, y.H, y.W, 256, st); }, "upsample2x");
+          b.op([=](cudaStream_t st) { return launch_upsample2x((const bf16*)y.p, (bf16*)up.p, B, y.H, y.W, 256, st); }, "upsample2x",
+               (double)y.elems() * 2 + (double)up.elems() * 2);
           x = up;
         } else {
           x = y;   // the last upsample is fused into the merge
@@ -391,7 +404,7 @@ int build_plan(dpb200_session* s) {
     b.op([=](cudaStream_t st) {
       return launch_decoder_merge((const bf16*)d2.p, (const bf16*)branch[0].p, (const bf16*)branch[1].p,
                                   (const bf16*)branch[2].p, (bf16*)merged.p, B, merged.H, merged.W, 256, st);
-    }, "decoder_merge");
+    }, "decoder_merge", (double)(d2.elems() + branch[0].elems() + branch[1].elems() + branch[2].elems() + merged.elems()) * 2);
     T4 dec = b.act(B, pf[0].H, pf[0].W, 256);
     { Builder::ConvOpt o; o.k = 1; b.conv("roi_heads.decoder.predictor", merged, dec, o); }
     b.tap("decoder", dec);
@@ -406,7 +419,7 @@ int build_plan(dpb200_session* s) {
     RoiAlignArgs a{};
     for (int l = 0; l < dp_levels; ++l) { a.feat[l] = (const bf16*)dp_feat[l].p; a.H[l] = dp_feat[l].H; a.W[l] = dp_feat[l].W; a.scale[l] = 1.0f / (float)(4 << l); }
     a.n_levels = dp_levels; a.C = 256; a.rois = s->rois_dp; a.n_rois = nv; a.R = Rd; a.P = P; a.out = dp_pooled.p;
-    b.op([a](cudaStream_t st) { return launch_roi_align(a, st); }, "roi_align_dp");
+    b.op([a](cudaStream_t st) { return launch_roi_align(a, st); }, "roi_align_dp", (double)dp_feat[0].elems() * 2 * dp_levels + (double)dp_pooled.elems() * 2);
   }
   b.tap("dp_pooled", dp_pooled);
   // ---- a16/a17 head
@@ -431,7 +444,8 @@ int build_plan(dpb200_session* s) {
       if (!w) return;
       const float* g = (const float*)w->d0; const float* be = (const float*)w->d1;
       const bf16* xp = (const bf16*)x.p; const int C = x.C; const int R_ = Rd;
-      b.op([=](cudaStream_t st) { return launch_groupnorm_relu(xp, g, be, y, R_, hw_in, C, ycs, hw_out, nv, st); }, "groupnorm_relu");
+      b.op([=](cudaStream_t st) { return launch_groupnorm_relu(xp, g, be, y, R_, hw_in, C, ycs, hw_out, nv, st); }, "groupnorm_relu",
+           (double)R_ * hw_in * C * 2 * 2 + (double)R_ * hw_out * C * 2);
     };
     // ASPP branches (deeplab.py:112-144); branch 3 (rate 56 >= P) only ever sees its centre tap
     const int dil[3] = {1, 6, 12};
@@ -482,7 +496,7 @@ int build_plan(dpb200_session* s) {
     b.op([ss, Rd, Kc, nv](cudaStream_t st) {
       return launch_predictor_upsample(ss->low, Rd, ss->low_S, ss->low_C, Kc, nv, ss->io->coarse, ss->io->fine,
                                        ss->io->u, ss->io->v, 1, st);
-    }, "predictor_upsample");
+    }, "predictor_upsample", (double)low.elems() * 4 + (double)Rd * (cfg.coarse_ch + 75) * (4.0 * P) * (4.0 * P) * 4);
   }
   return b.fail;
 }
@@ -612,6 +626,11 @@ int dpb200_session_profile(dpb200_session* s, const dpb200_forward_io* io, void*
   if (!rc) for (int i = 0; i < n; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
   for (auto& e2 : ev) cudaEventDestroy(e2);
   return rc;
+}
+int dpb200_session_op_bytes(const dpb200_session* s, int32_t i, double* bytes) {
+  if (!s || !bytes || i < 0 || i >= (int)s->ops.size()) { set_error("op_bytes: bad argument"); return -1; }
+  *bytes = s->op_bytes[i];
+  return 0;
 }
 double dpb200_session_flops(const dpb200_session* s) { return s ? s->flops : 0.0; }
 void dpb200_session_geometry(const dpb200_session* s, int32_t out[4]) {

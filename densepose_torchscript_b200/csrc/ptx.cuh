@@ -223,6 +223,11 @@ __device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 // (lo, hi) fp32 pair -> packed bf16x2 (lo in the low half), round to nearest even; _relu clamps at 0 first.
 __device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {
   uint32_t d;

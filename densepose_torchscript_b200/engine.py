@@ -88,6 +88,15 @@ class Session:
             out.append((buf.value.decode(), fl.value))
         return out
 
+    def op_bytes(self) -> List[float]:
+        """Algorithmic HBM bytes per launch (full detection capacity)."""
+        out = []
+        by = C.c_double()
+        for i in range(self.launches):
+            check(lib.dpb200_session_op_bytes(self.handle, i, C.byref(by)), "op_bytes")
+            out.append(by.value)
+        return out
+
     def profile(self, images: torch.Tensor, bgr: bool = True) -> List[float]:
         """One run with CUDA events around every launch (on the current stream); returns ms per launch."""
         self.io.images = images.data_ptr()

@@ -213,6 +213,10 @@ int dpb200_session_set_graph(dpb200_session* s, int32_t enable);
 int dpb200_session_launch_count(const dpb200_session* s);
 /* Name ("conv:<weight>" or the stage kernel) and padded-shape 2*MAC of launch i. */
 int dpb200_session_op_info(const dpb200_session* s, int32_t i, char* name, int32_t cap, double* flops);
+/* Algorithmic HBM bytes of launch i at full detection capacity: every operand read once (pixels a strided
+ * 1x1 conv skips excluded), every output written once; 0 for the latency-bound bookkeeping kernels. The
+ * roofline numerator of the memory-bound stages. */
+int dpb200_session_op_bytes(const dpb200_session* s, int32_t i, double* bytes);
 /* Like dpb200_session_run but brackets every launch with CUDA events on `stream`, synchronises, and writes
  * the per-launch milliseconds to ms[0..launch_count). Measurement aid for bench.py, not the serving path. */
 int dpb200_session_profile(dpb200_session* s, const dpb200_forward_io* io, void* stream, float* ms, int32_t cap);
