@@ -302,11 +302,13 @@ def run_ours(a):
     prof = [x / 3 for x in prof]
     if a.profile_out and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(a.profile_out)), exist_ok=True)
+    op_bytes = sess.op_bytes()
+    if a.profile_out and rank == 0:
         with open(a.profile_out, "w") as f:
-            json.dump([{"i": i, "name": n, "ms": ms, "padded_gflop": fl / 1e9} for i, ((n, fl), ms) in enumerate(zip(info, prof))], f, indent=0)
+            json.dump([{"i": i, "name": n, "ms": ms, "padded_gflop": fl / 1e9, "algorithmic_mb": by / 1e6}
+                       for i, ((n, fl), ms, by) in enumerate(zip(info, prof, op_bytes))], f, indent=0)
     conv_ms = sum(ms for (n, _), ms in zip(info, prof) if n.startswith("conv:"))
     total_ms = sum(prof)
-    op_bytes = sess.op_bytes()
     conv_gb = sum(b for (n, _), b in zip(info, op_bytes) if n.startswith("conv:")) / 1e9
 
     # max over ranks

@@ -91,8 +91,15 @@ static __device__ void nms_sorted_block(const float4* __restrict__ g_boxes, int 
           const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
           const float w_ = fmaxf(0.f, __fsub_rn(xx2, xx1)), h_ = fmaxf(0.f, __fsub_rn(yy2, yy1));
           const float inter = __fmul_rn(w_, h_);
-          const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, areas[j]), inter));
-          sup = ovr > thr;
+          const float uni = __fsub_rn(__fadd_rn(ai, areas[j]), inter);
+          // torchvision: inter / union > thr with an IEEE division. The quotient is only computed when the
+          // multiplied-out comparison is within 4e-6 of the boundary (or thr * union is not a normal positive
+          // number); everywhere else the two agree, so the mask is bit-identical at a fraction of the cost.
+          const float tu = __fmul_rn(thr, uni);
+          const bool normal = tu > 1.0e-30f && tu < 3.0e38f;     // no denormal / overflow / NaN corner
+          if (normal && inter > __fmul_rn(tu, 1.000004f)) sup = true;
+          else if (normal && inter < __fmul_rn(tu, 0.999996f)) sup = false;
+          else sup = __fdiv_rn(inter, uni) > thr;
         }
         const uint32_t bits = __ballot_sync(0xffffffffu, sup);
         if (lane == 0) mask[i * 32 + w] = bits;

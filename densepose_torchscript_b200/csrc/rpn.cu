@@ -58,6 +58,8 @@ rpn_topk_decode_kernel(RpnArgs a) {
   __shared__ unsigned long long keys[1024];
   __shared__ unsigned s_bin, s_above, s_cnt, s_eq_taken;
 
+  const int npix = L.H * L.W;
+  const float4* head4 = reinterpret_cast<const float4*>(head);
   auto key_at = [&](int i) -> uint32_t { return f2ord(__ldg(head + (long long)(i / 3) * 16 + (i % 3))); };
 
   uint32_t prefix = 0, mask = 0;
@@ -68,9 +70,12 @@ rpn_topk_decode_kernel(RpnArgs a) {
     const int nb = 1 << bits[pass];
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint32_t u = key_at(i);
-      if ((u & mask) == prefix) atomicAdd(&hist[(u >> shifts[pass]) & (nb - 1)], 1u);
+    for (int px = threadIdx.x; px < npix; px += blockDim.x) {
+      const float4 v = __ldg(head4 + (long long)px * 4);      // (logit a0, a1, a2, first delta): one 16-byte load
+      const uint32_t u0 = f2ord(v.x), u1 = f2ord(v.y), u2 = f2ord(v.z);
+      if ((u0 & mask) == prefix) atomicAdd(&hist[(u0 >> shifts[pass]) & (nb - 1)], 1u);
+      if ((u1 & mask) == prefix) atomicAdd(&hist[(u1 >> shifts[pass]) & (nb - 1)], 1u);
+      if ((u2 & mask) == prefix) atomicAdd(&hist[(u2 >> shifts[pass]) & (nb - 1)], 1u);
     }
     __syncthreads();
     // reversed bins: thread t owns reversed positions 2t, 2t+1 (bin = nb-1-pos)
@@ -97,11 +102,16 @@ rpn_topk_decode_kernel(RpnArgs a) {
   keys[threadIdx.x] = 0ull;
   __syncthreads();
   const bool take_all_eq = (eq_total == remaining);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const uint32_t u = key_at(i);
-    if (u > T || (take_all_eq && u == T)) {
-      const unsigned pos = atomicAdd(&s_cnt, 1u);
-      if (pos < 1024) keys[pos] = ((unsigned long long)u << 32) | (0xFFFFFFFFu - (uint32_t)i);
+  for (int px = threadIdx.x; px < npix; px += blockDim.x) {
+    const float4 v = __ldg(head4 + (long long)px * 4);
+    const uint32_t us[3] = {f2ord(v.x), f2ord(v.y), f2ord(v.z)};
+#pragma unroll
+    for (int an = 0; an < 3; ++an) {
+      const uint32_t u = us[an];
+      if (u > T || (take_all_eq && u == T)) {
+        const unsigned pos = atomicAdd(&s_cnt, 1u);
+        if (pos < 1024) keys[pos] = ((unsigned long long)u << 32) | (0xFFFFFFFFu - (uint32_t)(px * 3 + an));
+      }
     }
   }
   __syncthreads();
