@@ -152,7 +152,7 @@ int launch_roi_align(const RoiAlignArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------ box predictor tail
 
 __global__ void __launch_bounds__(1024)
-box_predict_kernel(BoxPredictArgs a) {
+box_predict_kernel(BoxPredictArgs a, int nc) {
   extern __shared__ uint32_t bp_smem[];
   // layout: [nms region (kNms)] [keys 1024 u64] [boxes 1024 float4] [scores 1024 f32]
   const int kNms = 1024 * 32 * 4 + 1024 * 16 + 1024 * 4 + 32 * 4;
@@ -160,7 +160,9 @@ box_predict_kernel(BoxPredictArgs a) {
   float4* sbox = reinterpret_cast<float4*>(keys + 1024);
   float* sscore = reinterpret_cast<float*>(sbox + 1024);
   __shared__ unsigned s_ncand, s_warp[32], s_total;
-  const int b = blockIdx.x, t = threadIdx.x;
+  // a cluster of nc CTAs per image: every CTA repeats the (cheap) score / decode / sort prologue, the IoU mask
+  // of the NMS is split over the cluster, CTA 0 finishes
+  const int b = blockIdx.x / nc, t = threadIdx.x;
   if (t == 0) s_ncand = 0;
   __syncthreads();
   const int np = a.prop_count[b] < a.R ? a.prop_count[b] : a.R;
@@ -213,7 +215,7 @@ box_predict_kernel(BoxPredictArgs a) {
     gk[t] = 0;
   }
   __syncthreads();
-  nms_sorted_block(gb, ncand, a.nms_thresh, gk, bp_smem);   // batched_nms with a single class
+  if (!nms_sorted_block(gb, ncand, a.nms_thresh, gk, bp_smem, nc)) return;   // batched_nms with a single class
   __syncthreads();
   // first `topk` kept, in score order
   const unsigned flag = (t < ncand && gk[t]) ? 1u : 0u;
@@ -261,15 +263,26 @@ static constexpr int kBoxPredictSmem = (1024 * 32 * 4 + 1024 * 16 + 1024 * 4 + 3
 
 int launch_box_predict(const BoxPredictArgs& a, cudaStream_t s) {
   if (a.R > 1024) { set_error("box_predict: R > 1024"); return -1; }
-  static bool once = false;
-  if (!once) {
+  static bool done[64] = {};
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!done[dev]) {
     cudaError_t e = cudaFuncSetAttribute(box_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kBoxPredictSmem);
     if (e != cudaSuccess) { set_error("box_predict smem: %s", cudaGetErrorString(e)); return -3; }
-    once = true;
+    done[dev] = true;
   }
-  box_predict_kernel<<<a.B, 1024, kBoxPredictSmem, s>>>(a);
-  DPB_CHECK_LAUNCH("box_predict");
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int nc = pick_nms_cluster(a.B, sms > 0 ? sms : 148);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(a.B * nc); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = kBoxPredictSmem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, box_predict_kernel, a, nc);
+  if (e != cudaSuccess) { set_error("box_predict launch: %s", cudaGetErrorString(e)); return -4; }
   return 0;
 }
 

@@ -178,42 +178,74 @@ int launch_rpn_topk_decode(const RpnArgs& a, cudaStream_t s) {
 
 static constexpr int kNmsSmem = 1024 * 32 * 4 + 1024 * 16 + 1024 * 4 + 32 * 4;
 
-__global__ void __launch_bounds__(1024) rpn_nms_kernel(RpnArgs a) {
+__global__ void __launch_bounds__(1024) rpn_nms_kernel(RpnArgs a, int nc) {
   extern __shared__ uint32_t nms_smem[];
-  const int lvl = blockIdx.x, b = blockIdx.y;
+  const int lvl = blockIdx.x / nc, b = blockIdx.y;       // a cluster of nc CTAs (along x) per (level, image)
   const int n = a.cand_count[b * 5 + lvl];
   const long long base = ((long long)b * 5 + lvl) * a.pre_topk;
   nms_sorted_block(reinterpret_cast<const float4*>(a.cand_boxes) + base, n, a.nms_thresh,
-                   a.cand_keep + base, nms_smem);
+                   a.cand_keep + base, nms_smem, nc);
 }
 
 __global__ void __launch_bounds__(1024)
-nms_sorted_kernel(const float4* boxes, int n, float thr, unsigned char* keep) {
+nms_sorted_kernel(const float4* boxes, int n, float thr, unsigned char* keep, int nc) {
   extern __shared__ uint32_t nms_smem[];
-  nms_sorted_block(boxes, n, thr, keep, nms_smem);
+  nms_sorted_block(boxes, n, thr, keep, nms_smem, nc);
 }
 
-static int ensure_smem(const void* fn, int bytes) {
+// opt-in dynamic shared memory, once per (kernel, device)
+static int ensure_smem(const void* fn, int bytes, bool* done_per_device) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (done_per_device[dev]) return 0;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return -3; }
+  done_per_device[dev] = true;
   return 0;
 }
 
+static int device_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// launch `fn` with clusters of nc CTAs along x
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_clustered(void (*fn)(KArgs...), dim3 grid, int threads, int smem, int nc, cudaStream_t s,
+                                    Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, fn, args...);
+}
+
 int launch_rpn_nms(const RpnArgs& a, cudaStream_t s) {
-  static bool once = false;
-  if (!once) { if (ensure_smem((const void*)rpn_nms_kernel, kNmsSmem)) return -3; once = true; }
-  dim3 grid(5, a.B);
-  rpn_nms_kernel<<<grid, 1024, kNmsSmem, s>>>(a);
-  DPB_CHECK_LAUNCH("rpn_nms");
+  static bool done[64] = {};
+  if (ensure_smem((const void*)rpn_nms_kernel, kNmsSmem, done)) return -3;
+  const int nc = pick_nms_cluster(5 * a.B, device_sms());
+  cudaError_t e = launch_clustered(rpn_nms_kernel, dim3(5 * nc, a.B), 1024, kNmsSmem, nc, s, a, nc);
+  if (e != cudaSuccess) { set_error("rpn_nms launch: %s", cudaGetErrorString(e)); return -4; }
   return 0;
 }
 
 int launch_nms_sorted(const float* boxes, int n, float thr, unsigned char* keep, cudaStream_t s) {
   if (n > 1024) { set_error("nms_sorted: n > 1024"); return -1; }
-  static bool once = false;
-  if (!once) { if (ensure_smem((const void*)nms_sorted_kernel, kNmsSmem)) return -3; once = true; }
-  nms_sorted_kernel<<<1, 1024, kNmsSmem, s>>>(reinterpret_cast<const float4*>(boxes), n, thr, keep);
-  DPB_CHECK_LAUNCH("nms_sorted");
+  static bool done[64] = {};
+  if (ensure_smem((const void*)nms_sorted_kernel, kNmsSmem, done)) return -3;
+  const int nc = 8;
+  cudaError_t e = launch_clustered(nms_sorted_kernel, dim3(nc), 1024, kNmsSmem, nc, s,
+                                   reinterpret_cast<const float4*>(boxes), n, thr, keep, nc);
+  if (e != cudaSuccess) { set_error("nms_sorted launch: %s", cudaGetErrorString(e)); return -4; }
   return 0;
 }
 
@@ -256,8 +288,8 @@ __global__ void __launch_bounds__(1024) rpn_merge_kernel(RpnArgs a) {
 
 int launch_rpn_merge(const RpnArgs& a, cudaStream_t s) {
   if (5 * a.pre_topk > 8192) { set_error("rpn_merge: too many candidates"); return -1; }
-  static bool once = false;
-  if (!once) { if (ensure_smem((const void*)rpn_merge_kernel, 8192 * 8)) return -3; once = true; }
+  static bool done[64] = {};
+  if (ensure_smem((const void*)rpn_merge_kernel, 8192 * 8, done)) return -3;
   rpn_merge_kernel<<<a.B, 1024, 8192 * 8, s>>>(a);
   DPB_CHECK_LAUNCH("rpn_merge");
   return 0;
