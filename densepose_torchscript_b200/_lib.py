@@ -101,7 +101,7 @@ class Weight(C.Structure):
 class ForwardIO(C.Structure):
     _fields_ = [
         ("images", vp), ("bgr", i32), ("pred_boxes", vp), ("scores", vp), ("det_count", vp), ("det_offsets", vp),
-        ("coarse", vp), ("fine", vp), ("u", vp), ("v", vp),
+        ("coarse", vp), ("fine", vp), ("u", vp), ("v", vp), ("out_half", i32),
     ]
 
 

@@ -134,7 +134,7 @@ int dpb200_avgpool(const void* x, void* y, int32_t r, int32_t hw, int32_t c, con
 int dpb200_predictor_upsample(const float* low, int32_t r, int32_t s, int32_t cpad, int32_t kc,
                               const int32_t* n_valid, float* coarse, float* fine, float* u, float* v,
                               int32_t planar, void* stream) {
-  return launch_predictor_upsample(low, r, s, cpad, kc, n_valid, coarse, fine, u, v, planar, S(stream));
+  return launch_predictor_upsample(low, r, s, cpad, kc, n_valid, coarse, fine, u, v, planar, 0, S(stream));
 }
 
 int dpb200_dp_resample(const dpb200_resample_args* a, void* stream) {

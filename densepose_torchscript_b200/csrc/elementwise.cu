@@ -4,6 +4,8 @@
 #include "conv_igemm.cuh"
 #include "ptx.cuh"
 
+#include <cuda_fp16.h>
+
 namespace dpb {
 
 static inline int grid_for(long long work, int threads, int cap = 148 * 16) {
@@ -441,10 +443,22 @@ predictor_upsample_kernel(const float* __restrict__ low, int S, int Cpad, int Kc
 // one 4-column strip and carries the horizontally interpolated row between them.
 static constexpr int kUpRows = 10;
 
+// four consecutive output values: fp32 (16-byte store) or fp16 (8-byte store, round to nearest even)
+__device__ __forceinline__ void store4(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void store4(__half* p, float a, float b, float c, float d) {
+  const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+  uint2 o;
+  o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = o;
+}
+
+template <typename OutT>
 __global__ void __launch_bounds__(256)
 predictor_upsample_planar_kernel(const float* __restrict__ low, int S, int Cpad, int Kc,
-                                 const int* __restrict__ n_valid, float* __restrict__ coarse,
-                                 float* __restrict__ fine, float* __restrict__ u, float* __restrict__ v) {
+                                 const int* __restrict__ n_valid, OutT* __restrict__ coarse,
+                                 OutT* __restrict__ fine, OutT* __restrict__ u, OutT* __restrict__ v) {
   const int r = blockIdx.y;
   if (n_valid != nullptr && r >= *n_valid) return;
   const int Sh = S >> 1, So = 2 * S;
@@ -456,12 +470,12 @@ predictor_upsample_planar_kernel(const float* __restrict__ low, int S, int Cpad,
   const int g = item % G;
   const int c = (item / G) % C;
   const int kb = item / (G * C);
-  float* dst; int cc, nc;
+  OutT* dst; int cc, nc;
   if (c < Kc) { dst = coarse; cc = c; nc = Kc; }
   else if (c < Kc + 25) { dst = fine; cc = c - Kc; nc = 25; }
   else if (c < Kc + 50) { dst = u; cc = c - Kc - 25; nc = 25; }
   else { dst = v; cc = c - Kc - 50; nc = 25; }
-  float* plane = dst + ((long long)r * nc + cc) * So * So + 4 * g;
+  OutT* plane = dst + ((long long)r * nc + cc) * So * So + 4 * g;
   const long long plane_sz = (long long)Sh * Sh;
   const float* lr = low + ((long long)r * 4 * Cpad + c) * plane_sz;     // + (py*2+px)*Cpad*plane_sz
   // low columns 2g-1, 2g, 2g+1, 2g+2 (clamped): (phase px, column xx) of each
@@ -488,15 +502,13 @@ predictor_upsample_planar_kernel(const float* __restrict__ low, int S, int Cpad,
     if (k > S - 1) break;
     hrow(k + 1, hi);
     if (k >= 0) {
-      *reinterpret_cast<float4*>(plane + (long long)(2 * k + 1) * So) =
-          make_float4(0.75f * lo[0] + 0.25f * hi[0], 0.75f * lo[1] + 0.25f * hi[1],
-                      0.75f * lo[2] + 0.25f * hi[2], 0.75f * lo[3] + 0.25f * hi[3]);
+      store4(plane + (long long)(2 * k + 1) * So, 0.75f * lo[0] + 0.25f * hi[0], 0.75f * lo[1] + 0.25f * hi[1],
+             0.75f * lo[2] + 0.25f * hi[2], 0.75f * lo[3] + 0.25f * hi[3]);
     }
     if (k < S - 1) {
       const float ly = (k < 0) ? 0.f : 0.75f, hy = 1.f - ly;
-      *reinterpret_cast<float4*>(plane + (long long)(2 * k + 2) * So) =
-          make_float4(hy * lo[0] + ly * hi[0], hy * lo[1] + ly * hi[1], hy * lo[2] + ly * hi[2],
-                      hy * lo[3] + ly * hi[3]);
+      store4(plane + (long long)(2 * k + 2) * So, hy * lo[0] + ly * hi[0], hy * lo[1] + ly * hi[1],
+             hy * lo[2] + ly * hi[2], hy * lo[3] + ly * hi[3]);
     }
 #pragma unroll
     for (int t = 0; t < 4; ++t) lo[t] = hi[t];
@@ -512,17 +524,24 @@ int stage_kernels_init() {
 }
 
 int launch_predictor_upsample(const float* low, int R, int S, int Cpad, int Kc, const int* n_valid,
-                              float* coarse, float* fine, float* u, float* v, int planar, cudaStream_t s) {
+                              void* coarse, void* fine, void* u, void* v, int planar, int out_half,
+                              cudaStream_t s) {
   if (planar) {
     if (S % 2 || Kc + 75 > Cpad) { set_error("predictor_upsample: bad shape S %d Cpad %d", S, Cpad); return -1; }
     if (R == 0) return 0;
     const int KB = (S + 1 + kUpRows - 1) / kUpRows;
     const int items = KB * (Kc + 75) * (S / 2);
     dim3 grid((items + 255) / 256, R);
-    predictor_upsample_planar_kernel<<<grid, 256, 0, s>>>(low, S, Cpad, Kc, n_valid, coarse, fine, u, v);
+    if (out_half)
+      predictor_upsample_planar_kernel<__half><<<grid, 256, 0, s>>>(low, S, Cpad, Kc, n_valid, (__half*)coarse,
+                                                                  (__half*)fine, (__half*)u, (__half*)v);
+    else
+      predictor_upsample_planar_kernel<float><<<grid, 256, 0, s>>>(low, S, Cpad, Kc, n_valid, (float*)coarse,
+                                                                 (float*)fine, (float*)u, (float*)v);
     DPB_CHECK_LAUNCH("predictor_upsample_planar");
     return 0;
   }
+  if (out_half) { set_error("predictor_upsample: fp16 output needs the phase-planar layout"); return -1; }
   if (S % 4 || Cpad % 4 || Kc + 75 > Cpad) { set_error("predictor_upsample: bad shape S %d Cpad %d", S, Cpad); return -1; }
   const size_t smem = (size_t)(kUpPairs + 1) * S * Cpad * sizeof(float);
   if (smem > kUpMaxSmem) { set_error("predictor_upsample: S %d Cpad %d needs %zu B of shared memory", S, Cpad, smem); return -1; }
@@ -535,7 +554,8 @@ int launch_predictor_upsample(const float* low, int R, int S, int Cpad, int Kc, 
   }
   if (R == 0) return 0;
   dim3 grid((S + 1 + kUpPairs - 1) / kUpPairs, R);
-  predictor_upsample_kernel<<<grid, 256, smem, s>>>(low, S, Cpad, Kc, n_valid, coarse, fine, u, v);
+  predictor_upsample_kernel<<<grid, 256, smem, s>>>(low, S, Cpad, Kc, n_valid, (float*)coarse, (float*)fine,
+                                                    (float*)u, (float*)v);
   DPB_CHECK_LAUNCH("predictor_upsample");
   return 0;
 }

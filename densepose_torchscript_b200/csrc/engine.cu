@@ -495,7 +495,7 @@ int build_plan(dpb200_session* s) {
     const int Kc = cfg.coarse_ch;
     b.op([ss, Rd, Kc, nv](cudaStream_t st) {
       return launch_predictor_upsample(ss->low, Rd, ss->low_S, ss->low_C, Kc, nv, ss->io->coarse, ss->io->fine,
-                                       ss->io->u, ss->io->v, 1, st);
+                                       ss->io->u, ss->io->v, 1, ss->io->out_half, st);
     }, "predictor_upsample", (double)low.elems() * 4 + (double)Rd * (cfg.coarse_ch + 75) * (4.0 * P) * (4.0 * P) * 4);
   }
   return b.fail;
@@ -547,7 +547,7 @@ void dpb200_session_destroy(dpb200_session* s) { delete s; }
 static bool same_io(const dpb200_forward_io& a, const dpb200_forward_io& b) {
   return a.images == b.images && a.bgr == b.bgr && a.pred_boxes == b.pred_boxes && a.scores == b.scores &&
          a.det_count == b.det_count && a.det_offsets == b.det_offsets && a.coarse == b.coarse &&
-         a.fine == b.fine && a.u == b.u && a.v == b.v;
+         a.fine == b.fine && a.u == b.u && a.v == b.v && a.out_half == b.out_half;
 }
 
 static int run_ops(dpb200_session* s, cudaStream_t st) {

@@ -104,7 +104,8 @@ int launch_avgpool(const bf16* x, bf16* y, int R, int HW, int C, const int* n_va
 // low: [R, S, S, Cpad] fp32 (channels: coarse[Kc], fine[25], u[25], v[25]); outputs [R, C, 2S, 2S].
 // planar != 0: low is [R, 2, 2, Cpad, S/2, S/2] (deconv output phases (py, px) as separate channel planes).
 int launch_predictor_upsample(const float* low, int R, int S, int Cpad, int Kc, const int* n_valid,
-                              float* coarse, float* fine, float* u, float* v, int planar, cudaStream_t s);
+                              void* coarse, void* fine, void* u, void* v, int planar, int out_half,
+                              cudaStream_t s);
 
 // Opt-in shared-memory attributes of the stage kernels on the current device (idempotent).
 int stage_kernels_init();

@@ -13,10 +13,12 @@ _DTYPES = {0: torch.bfloat16, 1: torch.float32, 2: torch.int32, 3: torch.uint8}
 
 
 class Session:
-    """Launch plan for one (batch, H0, W0, dtype) on one device."""
+    """Launch plan for one (batch, H0, W0, input dtype, output dtype) on one device. `out_half`: the four
+    DensePose tensors are produced as fp16 by the kernel itself (the reference's `.half()` contract)."""
 
-    def __init__(self, engine: "Engine", batch: int, h0: int, w0: int, src_u8: bool):
+    def __init__(self, engine: "Engine", batch: int, h0: int, w0: int, src_u8: bool, out_half: bool = False):
         self.engine, self.batch, self.h0, self.w0, self.src_u8 = engine, batch, h0, w0, src_u8
+        self.out_half = out_half
         spec = engine.spec
         nbytes = lib.dpb200_session_workspace_bytes(engine.handle, batch, h0, w0)
         if nbytes == 0:
@@ -34,15 +36,17 @@ class Session:
         self.scores = torch.zeros(batch, spec.dets_per_image, device=dev)
         self.det_count = torch.zeros(batch, dtype=torch.int32, device=dev)
         self.det_offsets = torch.zeros(batch + 1, dtype=torch.int32, device=dev)
-        self.coarse = torch.zeros(n, spec.coarse_ch, s, s, device=dev)
-        self.fine = torch.zeros(n, 25, s, s, device=dev)
-        self.u = torch.zeros(n, 25, s, s, device=dev)
-        self.v = torch.zeros(n, 25, s, s, device=dev)
+        odt = torch.float16 if out_half else torch.float32
+        self.coarse = torch.zeros(n, spec.coarse_ch, s, s, device=dev, dtype=odt)
+        self.fine = torch.zeros(n, 25, s, s, device=dev, dtype=odt)
+        self.u = torch.zeros(n, 25, s, s, device=dev, dtype=odt)
+        self.v = torch.zeros(n, 25, s, s, device=dev, dtype=odt)
         self.io = _lib.ForwardIO()
         self.io.pred_boxes = self.pred_boxes.data_ptr(); self.io.scores = self.scores.data_ptr()
         self.io.det_count = self.det_count.data_ptr(); self.io.det_offsets = self.det_offsets.data_ptr()
         self.io.coarse = self.coarse.data_ptr(); self.io.fine = self.fine.data_ptr()
         self.io.u = self.u.data_ptr(); self.io.v = self.v.data_ptr()
+        self.io.out_half = int(out_half)
         # launches go to a private stream (the legacy default stream cannot be graph-captured); run() orders
         # it after / before the caller's current stream with events, so the semantics stay "enqueued on the
         # current stream"
@@ -175,7 +179,7 @@ class Engine:
         with torch.cuda.device(self.device):
             check(lib.dpb200_model_create(C.byref(cfg), arr, len(packed), C.byref(h)), "dpb200_model_create")
         self.handle = h
-        self._sessions: Dict[Tuple[int, int, int, bool, int], Session] = {}
+        self._sessions: Dict[Tuple[int, int, int, bool, int, bool], Session] = {}
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -184,22 +188,24 @@ class Engine:
             lib.dpb200_model_destroy(h)
             self.handle = None
 
-    def session(self, batch: int, h0: int, w0: int, src_u8: bool = False, slot: int = 0) -> Session:
+    def session(self, batch: int, h0: int, w0: int, src_u8: bool = False, slot: int = 0,
+                out_half: bool = False) -> Session:
         """`slot` > 0 gives additional independent sessions (own workspace, outputs, stream) of the same shape."""
-        key = (batch, h0, w0, src_u8, slot)
+        key = (batch, h0, w0, src_u8, slot, out_half)
         s = self._sessions.get(key)
         if s is None:
             with torch.cuda.device(self.device):
-                s = Session(self, batch, h0, w0, src_u8)
+                s = Session(self, batch, h0, w0, src_u8, out_half)
             self._sessions[key] = s
         return s
 
-    def forward_batch(self, images: torch.Tensor, bgr: bool = True) -> List[Dict[str, torch.Tensor]]:
+    def forward_batch(self, images: torch.Tensor, bgr: bool = True, out_half: bool = False) -> List[Dict[str, torch.Tensor]]:
         """images [B,H,W,3] (HWC, fp32 or uint8) on any device -> list of reference-format result dicts."""
         images = images.to(self.device, non_blocking=True).contiguous()
         if images.dtype not in (torch.uint8, torch.float32):
             images = images.float()
-        s = self.session(images.shape[0], images.shape[1], images.shape[2], images.dtype == torch.uint8)
+        s = self.session(images.shape[0], images.shape[1], images.shape[2], images.dtype == torch.uint8,
+                         out_half=out_half)
         with torch.cuda.device(self.device):
             s.run(images, bgr)
         return s.results()
@@ -218,13 +224,14 @@ class HostPipeline:
     stream. Returned host tensors are views of the slot's pinned buffers: valid until that slot is reused.
     """
 
-    def __init__(self, engine: Engine, batch: int, h0: int, w0: int, src_u8: bool = False, depth: int = 2):
+    def __init__(self, engine: Engine, batch: int, h0: int, w0: int, src_u8: bool = False, depth: int = 2,
+                 out_half: bool = False):
         self.engine, self.depth = engine, depth
         self.slots = []
         dt = torch.uint8 if src_u8 else torch.float32
         with torch.cuda.device(engine.device):
             for i in range(depth):
-                sess = engine.session(batch, h0, w0, src_u8, slot=i + 1)
+                sess = engine.session(batch, h0, w0, src_u8, slot=i + 1, out_half=out_half)
                 dev_in = torch.empty(batch, h0, w0, 3, dtype=dt, device=engine.device)
                 host_in = torch.empty(batch, h0, w0, 3, dtype=dt).pin_memory()
                 outs_dev = [sess.pred_boxes, sess.scores, sess.det_count, sess.det_offsets, sess.coarse, sess.fine,
@@ -235,6 +242,15 @@ class HostPipeline:
         self.h2d_bytes = self.slots[0]["host_in"].numel() * self.slots[0]["host_in"].element_size()
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.slots[0]["outs_host"])
         self._next = 0
+
+    def close(self):
+        """Drops the slots' sessions (workspaces, output and staging buffers) from the engine."""
+        for sl in self.slots:
+            sess = sl["sess"]
+            for k, v in list(self.engine._sessions.items()):
+                if v is sess:
+                    del self.engine._sessions[k]
+        self.slots = []
 
     def _collect(self, sl) -> Optional[List[Dict[str, torch.Tensor]]]:
         if not sl["busy"]:

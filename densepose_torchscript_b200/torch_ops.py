@@ -104,8 +104,9 @@ def _forward_cuda(image, bgr, blob, table, names, cfg_i, cfg_f, dtype_probe):
         image = image.permute(1, 2, 0)
     if image.dtype != torch.uint8:
         image = image.float()
-    res = eng.forward_batch(image.unsqueeze(0), bgr)[0]
     dt = dtype_probe.dtype if dtype_probe.dtype in (torch.float16, torch.bfloat16) else torch.float32
+    # a `.half()` module gets its DensePose tensors as fp16 straight from the kernel (no conversion pass)
+    res = eng.forward_batch(image.unsqueeze(0), bgr, out_half=(dt == torch.float16))[0]
     return [res["image_size"], res["pred_boxes"].clone(), res["scores"].to(dt, copy=True), res["pred_classes"],
             res["pred_densepose_coarse_segm"].to(dt, copy=True), res["pred_densepose_fine_segm"].to(dt, copy=True),
             res["pred_densepose_u"].to(dt, copy=True), res["pred_densepose_v"].to(dt, copy=True)]

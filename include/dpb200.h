@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DPB200_ABI_VERSION 1
+#define DPB200_ABI_VERSION 2
 
 const char* dpb200_last_error(void);
 int dpb200_abi_version(void);
@@ -196,10 +196,12 @@ typedef struct dpb200_forward_io {
   float* scores;            /* [B, dets_per_image]                                                */
   int32_t* det_count;       /* [B]                                                                */
   int32_t* det_offsets;     /* [B+1] start of each image's rows in the packed DensePose tensors   */
-  float* coarse;            /* [B*dets_per_image, coarse_ch, 4S, 4S] packed, NCHW fp32            */
-  float* fine;              /* [B*dets_per_image, 25, 4S, 4S]                                     */
-  float* u;                 /* [B*dets_per_image, 25, 4S, 4S]                                     */
-  float* v;                 /* [B*dets_per_image, 25, 4S, 4S]                                     */
+  void* coarse;             /* [B*dets_per_image, coarse_ch, 4S, 4S] packed, NCHW fp32 (fp16: out_half) */
+  void* fine;               /* [B*dets_per_image, 25, 4S, 4S]                                     */
+  void* u;                  /* [B*dets_per_image, 25, 4S, 4S]                                     */
+  void* v;                  /* [B*dets_per_image, 25, 4S, 4S]                                     */
+  int32_t out_half;         /* != 0: the four DensePose tensors are written as IEEE fp16 (what the reference's
+                             * `.half()` module returns, run.py:20-29); boxes and scores stay fp32         */
 } dpb200_forward_io;
 int dpb200_session_run(dpb200_session* s, const dpb200_forward_io* io, void* stream);
 /* enable != 0: dpb200_session_run captures its launch sequence into a CUDA graph the first time it sees an

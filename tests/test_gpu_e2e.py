@@ -151,3 +151,17 @@ def test_uint8_input_session(s1x):
     # uint8 images are resized in uint8 by the reference (rounded); results stay close to the float path
     ia, ib = match_detections(r8["pred_boxes"], rf["pred_boxes"], 4.0)
     assert len(ia) >= 0.6 * len(rf["scores"])
+
+
+def test_half_outputs_are_the_rounded_fp32_outputs(s1x):
+    """out_half sessions (the reference's `.half()` output contract, run.py:20-29): the kernel writes fp16 itself;
+    every value must be the round-to-nearest-even fp16 of the fp32-output run, boxes / scores unchanged."""
+    eng, _ = s1x
+    img = W.synthetic_image(240, 600, seed=3)
+    r32 = {k: v.clone() for k, v in eng.forward_batch(img[None])[0].items()}
+    r16 = eng.forward_batch(img[None], out_half=True)[0]
+    assert len(r32["scores"]) > 0
+    assert torch.equal(r16["pred_boxes"], r32["pred_boxes"]) and torch.equal(r16["scores"], r32["scores"])
+    for k in DP:
+        assert r16[k].dtype == torch.float16
+        assert torch.equal(r16[k], r32[k].half()), k

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(_lib.lib, name), f"{name} is declared in dpb200.h but not exported by libdpb200.so"
     assert declared == set(_lib.EXPORTS)
-    assert _lib.lib.dpb200_abi_version() == 1
+    assert _lib.lib.dpb200_abi_version() == 2
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     for name in declared:
         assert re.search(rf"\bT {name}\b", out), name
