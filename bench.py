@@ -270,7 +270,41 @@ def run_ours(a):
         torch.cuda.empty_cache()
         return ms, h2d_, d2h_
 
+    def measure_e2e_extracted():
+        # run.py's flow as a pipeline: uint8 frames in (what cv2 hands run.py), forward, per-box resample + part
+        # argmax + U/V gather on the device, only boxes / scores / labels (u8) / uv at box resolution back
+        host_u8 = host.round().clamp(0, 255).to(torch.uint8).pin_memory()
+        pipe = HostPipeline(eng, B, H, W, True, depth=2, extract=True, labels_u8=True)
+        for _ in range(3):
+            pipe.submit(host_u8)
+        pipe.drain()
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for sl in pipe.slots:
+            sl["sess"].stream.wait_stream(torch.cuda.current_stream())
+        got, dets_, ex_bytes = 0, 0, []
+        for _ in range(a.steps):
+            r = pipe.submit(host_u8)
+            if r is not None:
+                got += len(r); dets_ += sum(len(x["densepose"]) for x in r); ex_bytes.append(pipe.extract_d2h_bytes)
+        for r in pipe.drain():
+            got += len(r); dets_ += sum(len(x["densepose"]) for x in r); ex_bytes.append(pipe.extract_d2h_bytes)
+        for sl in pipe.slots:
+            torch.cuda.current_stream().wait_stream(sl["sess"].stream)
+        e3.record()
+        barrier()
+        assert got == B * a.steps, (got, B, a.steps)
+        ms = e2.elapsed_time(e3)
+        small = pipe.d2h_bytes
+        h2d_ = pipe.h2d_bytes
+        pipe.close()
+        del pipe
+        torch.cuda.empty_cache()
+        return ms, h2d_, small + int(sum(ex_bytes) / max(len(ex_bytes), 1)), dets_ / max(got, 1)
+
     ms_e2e, h2d, d2h = measure_e2e(False)
+    ms_e2e_x, h2d_x, d2h_x, dets_x = measure_e2e_extracted()
     # the same with the DensePose tensors produced as fp16 by the kernel (what the reference's `.half()` module,
     # run.py's GPU default, returns): half the D2H bytes
     ms_e2e_half, _, d2h_half = measure_e2e(True)
@@ -322,12 +356,12 @@ def run_ours(a):
     conv_gb = sum(b for (n, _), b in zip(info, op_bytes) if n.startswith("conv:")) / 1e9
 
     # max over ranks
-    t = torch.tensor([ms_dev, ms_e2e, ms_e2e_half], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_dev, ms_e2e, ms_e2e_half, ms_e2e_x], device=dev, dtype=torch.float64)
     d = torch.tensor([dets], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(d, op=dist.ReduceOp.SUM)
-    ms_dev, ms_e2e, ms_e2e_half = float(t[0]), float(t[1]), float(t[2])
+    ms_dev, ms_e2e, ms_e2e_half, ms_e2e_x = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     total_dets = float(d[0])
 
     if rank == 0:
@@ -353,6 +387,12 @@ def run_ours(a):
                                  "d2h_bytes_per_step": d2h_half, "ms_per_step": ms_e2e_half / a.steps,
                                  "note": "same pipeline, DensePose tensors written as fp16 by the kernel (the output "
                                          "contract of the reference's .half() module, run.py:20-29); boxes / scores fp32"},
+            "e2e_extracted": {"value": n_img / (ms_e2e_x / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d_x,
+                              "d2h_bytes_per_step": d2h_x, "ms_per_step": ms_e2e_x / a.steps,
+                              "detections_per_image": dets_x,
+                              "note": "run.py's flow as a pipeline (HostPipeline(extract=True)): pinned uint8 frames in, "
+                                      "forward, DensePoseResultExtractor on the device (dpb200_dp_resample), only boxes, "
+                                      "scores, uint8 part labels and fp32 U/V at box resolution copied back"},
             "gpu_launches": sess.launches * a.steps,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,

@@ -80,7 +80,7 @@ class BoxPredictArgs(C.Structure):
 class ResampleArgs(C.Structure):
     _fields_ = [
         ("coarse", vp), ("fine", vp), ("u", vp), ("v", vp), ("d", i32), ("kc", i32), ("s", i32),
-        ("box_wh", vp), ("offsets", vp), ("labels", vp), ("uv", vp), ("total_pixels", i64),
+        ("box_wh", vp), ("offsets", vp), ("labels", vp), ("uv", vp), ("total_pixels", i64), ("labels_u8", i32),
     ]
 
 

@@ -141,8 +141,8 @@ int dpb200_dp_resample(const dpb200_resample_args* a, void* stream) {
   if (!a) { set_error("dp_resample: null args"); return -1; }
   ResampleArgs r{};
   r.coarse = a->coarse; r.fine = a->fine; r.u = a->u; r.v = a->v; r.D = a->d; r.Kc = a->kc; r.S = a->s;
-  r.box_wh = a->box_wh; r.offsets = (const long long*)a->offsets; r.labels = (long long*)a->labels;
-  r.uv = a->uv; r.total_pixels = a->total_pixels;
+  r.box_wh = a->box_wh; r.offsets = (const long long*)a->offsets; r.labels = a->labels;
+  r.uv = a->uv; r.total_pixels = a->total_pixels; r.labels_u8 = a->labels_u8;
   return launch_dp_resample(r, S(stream));
 }
 

@@ -116,9 +116,10 @@ struct ResampleArgs {
   int D, Kc, S;
   const int* box_wh;        // [D, 2] (w, h) already max(int, 1)  (host computed from boxes)
   const long long* offsets; // [D + 1] pixel offsets into the packed outputs
-  long long* labels;        // packed int64 [sum h*w]
+  void* labels;             // packed int64 [sum h*w] (uint8 when labels_u8)
   float* uv;                // packed fp32 [sum 2*h*w] (box i at 2*offsets[i]: u plane then v plane)
   long long total_pixels;
+  int labels_u8;            // part labels are 0..24: one byte each instead of the reference's int64
 };
 int launch_dp_resample(const ResampleArgs& a, cudaStream_t s);
 

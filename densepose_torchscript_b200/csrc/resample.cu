@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(256) dp_resample_kernel(ResampleArgs a) {
       if (v > fbest) { fbest = v; farg = c; }
     }
     const int label = (carg > 0) ? farg : 0;
-    a.labels[p] = (long long)label;
+    if (a.labels_u8) reinterpret_cast<unsigned char*>(a.labels)[p] = (unsigned char)label;
+    else reinterpret_cast<long long*>(a.labels)[p] = (long long)label;
     float uu = 0.f, vv = 0.f;
     if (label > 0) {
       uu = sample(a.u + ((long long)d * 25 + label) * plane);

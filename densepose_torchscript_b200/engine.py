@@ -222,11 +222,21 @@ class HostPipeline:
 
     Every submit() enqueues H2D copy -> forward -> D2H copy of the reference-format outputs on the slot's
     stream. Returned host tensors are views of the slot's pinned buffers: valid until that slot is reused.
+
+    extract=True is the run.py flow (run.py:33-57 + visualizer.py:46-56) as a pipeline: only boxes / scores /
+    counts come back after the forward; when a slot is collected, the per-box resample + part argmax + U/V gather
+    (`dpb200_dp_resample`) runs on the device over that batch's detections and only `labels` (uint8, or int64
+    like the reference with labels_u8=False) and `uv` at box resolution cross PCIe. Each result dict then holds
+    pred_boxes, scores, boxes_xywh and `densepose` = [{'labels': [h,w], 'uv': [2,h,w]} per detection].
     """
 
     def __init__(self, engine: Engine, batch: int, h0: int, w0: int, src_u8: bool = False, depth: int = 2,
-                 out_half: bool = False):
+                 out_half: bool = False, extract: bool = False, labels_u8: bool = True):
         self.engine, self.depth = engine, depth
+        self.extract, self.labels_u8 = extract, labels_u8
+        if extract and out_half:
+            raise ValueError("extract=True reads the fp32 DensePose tensors on the device; out_half is for full outputs")
+        self.extract_d2h_bytes = 0          # bytes of the last collected extraction (data dependent)
         self.slots = []
         dt = torch.uint8 if src_u8 else torch.float32
         with torch.cuda.device(engine.device):
@@ -234,11 +244,13 @@ class HostPipeline:
                 sess = engine.session(batch, h0, w0, src_u8, slot=i + 1, out_half=out_half)
                 dev_in = torch.empty(batch, h0, w0, 3, dtype=dt, device=engine.device)
                 host_in = torch.empty(batch, h0, w0, 3, dtype=dt).pin_memory()
-                outs_dev = [sess.pred_boxes, sess.scores, sess.det_count, sess.det_offsets, sess.coarse, sess.fine,
-                            sess.u, sess.v]
+                outs_dev = [sess.pred_boxes, sess.scores, sess.det_count, sess.det_offsets]
+                if not extract:
+                    outs_dev += [sess.coarse, sess.fine, sess.u, sess.v]
                 outs_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs_dev]
                 self.slots.append(dict(sess=sess, dev_in=dev_in, host_in=host_in, outs_dev=outs_dev,
-                                       outs_host=outs_host, done=torch.cuda.Event(), busy=False))
+                                       outs_host=outs_host, done=torch.cuda.Event(), busy=False,
+                                       ex_dev=None, ex_host=None))
         self.h2d_bytes = self.slots[0]["host_in"].numel() * self.slots[0]["host_in"].element_size()
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.slots[0]["outs_host"])
         self._next = 0
@@ -257,6 +269,8 @@ class HostPipeline:
             return None
         sl["done"].synchronize()
         sl["busy"] = False
+        if self.extract:
+            return self._collect_extracted(sl)
         boxes, scores, counts, offs, coarse, fine, u, v = sl["outs_host"]
         sess = sl["sess"]
         out = []
@@ -267,6 +281,48 @@ class HostPipeline:
                         "pred_classes": torch.zeros(d, dtype=torch.int64),
                         "pred_densepose_coarse_segm": coarse[o:o + d], "pred_densepose_fine_segm": fine[o:o + d],
                         "pred_densepose_u": u[o:o + d], "pred_densepose_v": v[o:o + d]})
+        return out
+
+    def _collect_extracted(self, sl) -> List[Dict[str, object]]:
+        from . import ops
+        boxes, scores, counts, offs = sl["outs_host"]
+        sess = sl["sess"]
+        dev = self.engine.device
+        cnt = [int(c) for c in counts]
+        # packed detection order = the packed DensePose rows (det_offsets)
+        packed = torch.cat([boxes[b, :cnt[b]] for b in range(sess.batch)]) if sum(cnt) else boxes.new_zeros((0, 4))
+        boxes_xywh, wh, offsets = ops.box_sizes(packed)
+        total = int(offsets[-1])
+        lab_dt = torch.uint8 if self.labels_u8 else torch.int64
+        lab_b = 1 if self.labels_u8 else 8
+        ex_dev, ex_host = sl["ex_dev"], sl["ex_host"]
+        if ex_dev is None or ex_dev[0].numel() < total:
+            cap = max(int(total * 1.25), 1 << 20)
+            with torch.cuda.device(dev):
+                ex_dev = (torch.empty(cap, dtype=lab_dt, device=dev), torch.empty(2 * cap, dtype=torch.float32, device=dev))
+            ex_host = (torch.empty(cap, dtype=lab_dt).pin_memory(), torch.empty(2 * cap, dtype=torch.float32).pin_memory())
+            sl["ex_dev"], sl["ex_host"] = ex_dev, ex_host
+        n = int(sum(cnt))
+        if n and total:
+            with torch.cuda.device(dev), torch.cuda.stream(sess.stream):
+                wh_d = wh.to(dev, non_blocking=True)
+                off_d = offsets.to(dev, non_blocking=True)
+                ops.dp_resample_into(sess.coarse[:n], sess.fine[:n], sess.u[:n], sess.v[:n], wh_d, off_d, total,
+                                     ex_dev[0], ex_dev[1], stream=C.c_void_p(sess.stream.cuda_stream))
+                ex_host[0][:total].copy_(ex_dev[0][:total], non_blocking=True)
+                ex_host[1][:2 * total].copy_(ex_dev[1][:2 * total], non_blocking=True)
+            sess.stream.synchronize()
+        self.extract_d2h_bytes = total * (lab_b + 8)
+        out, k = [], 0
+        for b in range(sess.batch):
+            dens = []
+            for _ in range(cnt[b]):
+                w, h, o = int(wh[k, 0]), int(wh[k, 1]), int(offsets[k])
+                dens.append({"labels": ex_host[0][o:o + h * w].view(h, w), "uv": ex_host[1][2 * o:2 * o + 2 * h * w].view(2, h, w)})
+                k += 1
+            out.append({"image_size": torch.tensor([sess.h0, sess.w0], dtype=torch.int64),
+                        "pred_boxes": boxes[b, :cnt[b]], "scores": scores[b, :cnt[b]],
+                        "boxes_xywh": boxes_xywh[k - cnt[b]:k], "densepose": dens})
         return out
 
     def submit(self, images: torch.Tensor, bgr: bool = True):

@@ -243,29 +243,43 @@ def predictor_upsample(low: torch.Tensor, kc: int, planar: bool = False):
     return outs
 
 
-def dp_resample(coarse: torch.Tensor, fine: torch.Tensor, u: torch.Tensor, v: torch.Tensor,
-                boxes_xyxy: torch.Tensor):
-    """DensePoseResultExtractor on the device. Returns (list of {'labels','uv'} per box, boxes_xywh)."""
-    _lib.require_device()
-    d = boxes_xyxy.shape[0]
-    dev = coarse.device
+def box_sizes(boxes_xyxy: torch.Tensor):
+    """Host-side geometry of the extractor (visualizer.py:40-43,20-30): xywh, `.long()` truncation, max(int, 1).
+    Returns (boxes_xywh, wh int32 [D,2] on the CPU, pixel offsets int64 [D+1] on the CPU)."""
     boxes_xywh = boxes_xyxy.clone()
     boxes_xywh[:, 2:] -= boxes_xywh[:, :2]                       # visualizer.py:41-42
     wh = boxes_xywh[:, 2:].long().clamp(min=1).to(torch.int32).cpu()   # .long() truncation, max(int, 1)
     sizes = (wh[:, 0].long() * wh[:, 1].long())
-    offsets = torch.zeros(d + 1, dtype=torch.int64)
+    offsets = torch.zeros(boxes_xyxy.shape[0] + 1, dtype=torch.int64)
     offsets[1:] = torch.cumsum(sizes, 0)
+    return boxes_xywh, wh, offsets
+
+
+def dp_resample_into(coarse, fine, u, v, wh_dev: torch.Tensor, off_dev: torch.Tensor, total: int,
+                     labels: torch.Tensor, uv: torch.Tensor, stream=None):
+    """Launches the extractor kernel into caller-owned packed buffers (labels int64 or uint8, uv fp32)."""
+    a = _lib.ResampleArgs()
+    a.coarse, a.fine, a.u, a.v = coarse.data_ptr(), fine.data_ptr(), u.data_ptr(), v.data_ptr()
+    a.d, a.kc, a.s = wh_dev.shape[0], coarse.shape[1], coarse.shape[2]
+    a.box_wh, a.offsets, a.labels, a.uv, a.total_pixels = (wh_dev.data_ptr(), off_dev.data_ptr(), labels.data_ptr(),
+                                                           uv.data_ptr(), total)
+    a.labels_u8 = int(labels.dtype == torch.uint8)
+    check(lib.dpb200_dp_resample(C.byref(a), stream if stream is not None else _stream()), "dpb200_dp_resample")
+
+
+def dp_resample(coarse: torch.Tensor, fine: torch.Tensor, u: torch.Tensor, v: torch.Tensor,
+                boxes_xyxy: torch.Tensor, labels_u8: bool = False):
+    """DensePoseResultExtractor on the device. Returns (list of {'labels','uv'} per box, boxes_xywh)."""
+    _lib.require_device()
+    d = boxes_xyxy.shape[0]
+    dev = coarse.device
+    boxes_xywh, wh, offsets = box_sizes(boxes_xyxy)
     total = int(offsets[-1])
-    labels = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+    labels = torch.empty(max(total, 1), dtype=torch.uint8 if labels_u8 else torch.int64, device=dev)
     uv = torch.empty(max(2 * total, 1), dtype=torch.float32, device=dev)
     if d and total:
-        a = _lib.ResampleArgs()
-        wh_d, off_d = wh.to(dev).contiguous(), offsets.to(dev)
-        a.coarse, a.fine, a.u, a.v = (coarse.contiguous().data_ptr(), fine.contiguous().data_ptr(),
-                                      u.contiguous().data_ptr(), v.contiguous().data_ptr())
-        a.d, a.kc, a.s = d, coarse.shape[1], coarse.shape[2]
-        a.box_wh, a.offsets, a.labels, a.uv, a.total_pixels = wh_d.data_ptr(), off_d.data_ptr(), labels.data_ptr(), uv.data_ptr(), total
-        check(lib.dpb200_dp_resample(C.byref(a), _stream()), "dpb200_dp_resample")
+        dp_resample_into(coarse.contiguous(), fine.contiguous(), u.contiguous(), v.contiguous(),
+                         wh.to(dev).contiguous(), offsets.to(dev), total, labels, uv)
     results = []
     for i in range(d):
         w, h = int(wh[i, 0]), int(wh[i, 1])

@@ -143,12 +143,13 @@ int dpb200_predictor_upsample(const float* low, int32_t r, int32_t s, int32_t cp
                               int32_t planar, void* stream);
 
 /* DensePoseResultExtractor (visualizer.py:10-56): per-box resize + argmax + U/V gather.
- * box_wh [D,2] = (max(int(w),1), max(int(h),1)); offsets [D+1] pixel prefix sums; labels int64 packed;
- * uv fp32 packed (box i at 2*offsets[i]: U plane then V plane). */
+ * box_wh [D,2] = (max(int(w),1), max(int(h),1)); offsets [D+1] pixel prefix sums; labels int64 packed
+ * (one uint8 each when labels_u8 != 0: part labels are 0..24); uv fp32 packed (box i at 2*offsets[i]: U plane
+ * then V plane). */
 typedef struct dpb200_resample_args {
   const float* coarse; const float* fine; const float* u; const float* v;
   int32_t d, kc, s; const int32_t* box_wh; const int64_t* offsets;
-  int64_t* labels; float* uv; int64_t total_pixels;
+  void* labels; float* uv; int64_t total_pixels; int32_t labels_u8;
 } dpb200_resample_args;
 int dpb200_dp_resample(const dpb200_resample_args* a, void* stream);
 

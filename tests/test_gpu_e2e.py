@@ -165,3 +165,28 @@ def test_half_outputs_are_the_rounded_fp32_outputs(s1x):
     for k in DP:
         assert r16[k].dtype == torch.float16
         assert torch.equal(r16[k], r32[k].half()), k
+
+
+def test_pipelined_extractor_matches_the_extractor_on_full_outputs(s1x):
+    """HostPipeline(extract=True) (run.py flow: forward -> per-box resample / argmax / UV gather on the device, only
+    labels + uv cross PCIe) against DensePoseResultExtractor applied to the full output tensors: bit-equal."""
+    from densepose_torchscript_b200.engine import HostPipeline
+    from densepose_torchscript_b200.extractor import DensePoseResultExtractor
+    eng, _ = s1x
+    imgs = torch.stack([W.synthetic_image(240, 600, seed=3), W.synthetic_image(240, 600, seed=4)])
+    full = [{k: v.clone() for k, v in r.items()} for r in eng.forward_batch(imgs)]
+    for u8 in (True, False):
+        pipe = HostPipeline(eng, 2, 240, 600, False, depth=2, extract=True, labels_u8=u8)
+        assert pipe.submit(imgs) is None
+        (res,) = pipe.drain()
+        assert pipe.extract_d2h_bytes > 0
+        for b in range(2):
+            ref, xywh = DensePoseResultExtractor()(full[b])
+            assert torch.equal(res[b]["pred_boxes"], full[b]["pred_boxes"].cpu())
+            assert torch.equal(res[b]["boxes_xywh"], xywh.cpu())
+            assert len(res[b]["densepose"]) == len(ref) > 0
+            for got, want in zip(res[b]["densepose"], ref):
+                assert got["labels"].dtype == (torch.uint8 if u8 else torch.int64)
+                assert torch.equal(got["labels"].long(), want["labels"].cpu())
+                assert torch.equal(got["uv"], want["uv"].cpu())
+        pipe.close()
