@@ -190,3 +190,25 @@ def test_pipelined_extractor_matches_the_extractor_on_full_outputs(s1x):
                 assert torch.equal(got["labels"].long(), want["labels"].cpu())
                 assert torch.equal(got["uv"], want["uv"].cpu())
         pipe.close()
+
+
+def test_1080p_frames_r101(tmp_path):
+    """configs[3]: R_101_FPN_s1x on 1080x1920 video frames (-> 749x1333 -> padded 768x1344):
+    geometry, shapes, clipping to the frame, uint8 frames and batch independence at that size."""
+    eng, _ = _engine("densepose_rcnn_R_101_FPN_s1x")
+    frames = torch.stack([W.synthetic_image(1080, 1920, seed=11), W.synthetic_image(1080, 1920, seed=12)])
+    sess = eng.session(2, 1080, 1920, False)
+    assert (sess.hr, sess.wr, sess.hp, sess.wp) == (749, 1333, 768, 1344)
+    res = [{k: v.clone() for k, v in r.items()} for r in eng.forward_batch(frames)]
+    for r in res:
+        d = len(r["scores"])
+        assert 0 < d <= 100 and r["pred_densepose_u"].shape == (d, 25, 112, 112)
+        assert torch.equal(r["image_size"].cpu(), torch.tensor([1080, 1920]))
+        bx = r["pred_boxes"]
+        assert float(bx.min()) >= 0 and float(bx[:, 0::2].max()) <= 1920 and float(bx[:, 1::2].max()) <= 1080
+        assert bool(torch.isfinite(r["pred_densepose_fine_segm"]).all())
+    single = eng.forward_batch(frames[1:2])[0]
+    for k in single:
+        assert torch.equal(single[k], res[1][k]), k
+    r8 = eng.forward_batch(frames[:1].round().clamp(0, 255).to(torch.uint8))[0]
+    assert r8["pred_densepose_u"].shape[1:] == (25, 112, 112)

@@ -203,6 +203,43 @@ def test_nms_keep_order_bitexact(ops, n, thr, seed):
     assert torch.equal(torch.nonzero(got).squeeze(1), ref_keep)
 
 
+def test_nms_threshold_boundary_and_degenerate_sets(ops):
+    """The device kernel only computes the IEEE quotient near the threshold; these sets sit on it: integer-grid
+    boxes whose IoU is exactly 1/2, 1/3, 2/3 (kept when == thr, torchvision uses a strict >), IoUs one ulp either
+    side, 1000 identical boxes (one survivor), a suppression chain, and huge coordinates."""
+    def run(boxes, thr):
+        scores = torch.arange(boxes.shape[0], 0, -1).float()           # already sorted
+        ref = O.nms(boxes, scores, thr)
+        got = ops.nms_sorted(boxes.cuda(), thr).cpu()
+        assert torch.equal(torch.nonzero(got).squeeze(1), ref), (thr, boxes.shape)
+
+    # pairs (0,0,w,1) and (s,0,s+w,1): inter = w-s, union = w+s  ->  IoU = (w-s)/(w+s)
+    rows = []
+    for w, s_ in [(3, 1), (2, 1), (5, 1), (4, 2), (6, 2), (7, 3), (9, 3), (100, 50), (3, 0)]:
+        y = 10.0 * len(rows)
+        rows += [[0.0, y, float(w), y + 1.0], [float(s_), y, float(s_ + w), y + 1.0]]
+    grid = torch.tensor(rows)
+    for thr in (0.5, 1.0 / 3.0, 2.0 / 3.0, 0.7, 0.3, 0.0, 1.0):
+        run(grid, thr)
+    # thresholds one ulp either side of exactly representable IoUs
+    for base in (0.5, 0.25, 0.75):
+        t = torch.tensor(base)
+        for thr in (float(torch.nextafter(t, torch.tensor(0.0))), float(torch.nextafter(t, torch.tensor(1.0)))):
+            run(grid, thr)
+    g = torch.Generator().manual_seed(5)
+    # dense random set with many IoUs close to the threshold: jittered copies of a few boxes
+    base = torch.tensor([[10.0, 10.0, 110.0, 60.0], [50.0, 20.0, 150.0, 90.0], [0.0, 0.0, 40.0, 200.0]])
+    jit = base[torch.randint(0, 3, (1000,), generator=g)] + torch.rand(1000, 4, generator=g) * 60.0
+    jit[:, 2:] = torch.maximum(jit[:, 2:], jit[:, :2])
+    for thr in (0.5, 0.7):
+        run(jit, thr)
+    run(base[:1].repeat(1000, 1), 0.5)                                          # all identical
+    chain = torch.stack([torch.tensor([float(i), 0.0, float(i) + 10.0, 10.0]) for i in range(1000)])
+    run(chain, 0.7)                                                             # sliding chain of overlaps
+    run(jit * 1.0e18, 0.5)                                                      # areas ~1e40: overflow to inf
+    run(jit * 1.0e-22, 0.5)                                                     # areas in the denormal range
+
+
 # ----------------------------------------------------------------------------------------------- ROIAlign
 def test_roi_align_multilevel_bitexact(ops):
     g = torch.Generator().manual_seed(21)
