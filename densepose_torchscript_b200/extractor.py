@@ -38,11 +38,16 @@ class End2EndVisualizer:
         self.inplace = inplace
 
     def visualize(self, image_bgr: Any, outputs: Dict[str, torch.Tensor]):
+        img = image_bgr if self.inplace else image_bgr.copy()
+        results, boxes_xywh = self.extractor(outputs)
+        return self.draw(img, results, boxes_xywh)
+
+    def draw(self, img: Any, results: List[Dict[str, torch.Tensor]], boxes_xywh: torch.Tensor):
+        """Blends already extracted per-box results (from DensePoseResultExtractor or from
+        HostPipeline(extract=True), whose `densepose` / `boxes_xywh` entries have this form) into `img`."""
         import cv2
         import numpy as np
 
-        img = image_bgr if self.inplace else image_bgr.copy()
-        results, boxes_xywh = self.extractor(outputs)
         boxes = boxes_xywh.long().cpu().tolist()
         for res, (x, y, w, h) in zip(results, boxes):
             labels = res["labels"].to(torch.uint8).cpu().numpy()

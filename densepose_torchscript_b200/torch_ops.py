@@ -92,6 +92,15 @@ def _engine_for(blob: torch.Tensor, table: List[int], names: List[str], cfg_i: L
     return eng
 
 
+def engine_of(module) -> Engine:
+    """The Engine behind a (scripted or eager, already `.cuda()`) DensePoseB200Predictor: lets a caller that holds
+    only the exported model batch frames through HostPipeline (run.py's video path)."""
+    blob = module.weights
+    if not blob.is_cuda:
+        raise _lib.DPB200Error("engine_of: move the module to a B200 first (.cuda())")
+    return _engine_for(blob, list(module.table), list(module.names), list(module.cfg_i), list(module.cfg_f))
+
+
 def _forward_cuda(image, bgr, blob, table, names, cfg_i, cfg_f, dtype_probe):
     if not blob.is_cuda:
         raise _lib.DPB200Error("dpb200::forward has no CPU implementation: move the module to a B200 (.cuda())")

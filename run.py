@@ -10,6 +10,7 @@ import argparse
 import os
 
 import cv2
+import numpy as np
 import torch
 
 import densepose_torchscript_b200.torch_ops  # noqa: F401  registers torch.ops.dpb200 before torch.jit.load
@@ -22,6 +23,7 @@ def main():
     parser.add_argument("input", type=str, help="Path to the input image or video")
     parser.add_argument("--cpu", action="store_true", help="(unsupported) the engine has no CPU path")
     parser.add_argument("--fp32", action="store_true", help="Emit fp32 outputs on the GPU")
+    parser.add_argument("--batch", type=int, default=8, help="video frames per engine batch (the reference is 1)")
     args = parser.parse_args()
 
     predictor = torch.jit.load(args.model).eval()
@@ -42,22 +44,72 @@ def main():
     if not cap.isOpened():
         raise SystemExit(f"cannot read {args.input} as an image or a video")
     fps = cap.get(cv2.CAP_PROP_FPS) or 25.0
-    writer = None
-    n = 0
+    n = run_video(cap, predictor, visualizer, save_path, fps, args.batch)
+    cap.release()
+    print(f"Video ({n} frames) saved to {save_path}")
+
+
+def run_video(cap, predictor, visualizer, save_path, fps, batch):
+    """The reference steps a video frame by frame (run.py:42-57). Same output here, but frames go through the
+    engine in batches: uint8 frames -> pinned staging -> device resize/normalise -> forward -> on-device result
+    extraction, double-buffered (HostPipeline), so decode / draw on the host overlap the GPU."""
+    from densepose_torchscript_b200.engine import HostPipeline
+    from densepose_torchscript_b200.torch_ops import engine_of
+
+    eng = engine_of(predictor)
+    writer, pipe, n = None, None, 0
+    pending = []          # frame batches in flight, oldest first
+
+    def emit(frames, results):
+        nonlocal writer, n
+        for frame, res in zip(frames, results):
+            out = visualizer.draw(frame, res["densepose"], res["boxes_xywh"])
+            if writer is None:
+                writer = cv2.VideoWriter(save_path, cv2.VideoWriter_fourcc(*"mp4v"), fps, (out.shape[1], out.shape[0]))
+            writer.write(out)
+            n += 1
+
+    def flush_tail(frames):
+        # fewer frames than a batch: one at a time through the exported module, like the reference
+        for frame in frames:
+            emit([frame], [_single(predictor, visualizer, frame)])
+
+    buf = []
     while True:
         ok, frame = cap.read()
+        if ok:
+            buf.append(frame)
+        if len(buf) == batch or (not ok and buf):
+            if len(buf) < batch:
+                if pipe is not None:
+                    for frames, res in zip(pending, pipe.drain()):
+                        emit(frames, res)
+                    pending.clear()
+                flush_tail(buf)
+                buf = []
+            else:
+                if pipe is None:
+                    h, w = buf[0].shape[:2]
+                    pipe = HostPipeline(eng, batch, h, w, src_u8=True, depth=2, extract=True, labels_u8=True)
+                done = pipe.submit(torch.from_numpy(np.stack(buf)))
+                pending.append(buf)
+                buf = []
+                if done is not None:
+                    emit(pending.pop(0), done)
         if not ok:
             break
-        outputs = predictor(torch.from_numpy(frame))
-        frame = visualizer.visualize(frame, outputs)
-        if writer is None:
-            writer = cv2.VideoWriter(save_path, cv2.VideoWriter_fourcc(*"mp4v"), fps, (frame.shape[1], frame.shape[0]))
-        writer.write(frame)
-        n += 1
-    cap.release()
+    if pipe is not None:
+        for frames, res in zip(pending, pipe.drain()):
+            emit(frames, res)
     if writer is not None:
         writer.release()
-    print(f"Video ({n} frames) saved to {save_path}")
+    return n
+
+
+def _single(predictor, visualizer, frame):
+    outputs = predictor(torch.from_numpy(frame))
+    results, boxes_xywh = visualizer.extractor({k: v.float() if v.is_floating_point() else v for k, v in outputs.items()})
+    return {"densepose": results, "boxes_xywh": boxes_xywh}
 
 
 if __name__ == "__main__":
