@@ -212,3 +212,16 @@ def test_1080p_frames_r101(tmp_path):
         assert torch.equal(single[k], res[1][k]), k
     r8 = eng.forward_batch(frames[:1].round().clamp(0, 255).to(torch.uint8))[0]
     assert r8["pred_densepose_u"].shape[1:] == (25, 112, 112)
+
+
+def test_session_cache_is_bounded(s1x):
+    """A stream of differently sized images must not accumulate workspaces: the engine keeps max_sessions plain
+    sessions and drops the least recently used."""
+    from densepose_torchscript_b200.config import BUILTIN
+    from densepose_torchscript_b200.engine import Engine
+    eng = Engine(BUILTIN["densepose_rcnn_R_50_FPN_s1x"], packed=s1x[0].packed, max_sessions=2)
+    for h, w in ((64, 96), (96, 64), (80, 80), (64, 96)):
+        r = eng.forward_batch(W.synthetic_image(h, w, seed=h)[None])[0]
+        assert r["image_size"].tolist() == [h, w]
+        assert len(eng._sessions) <= 2
+    assert (1, 64, 96, False, 0, False) in eng._sessions and (1, 80, 80, False, 0, False) in eng._sessions
