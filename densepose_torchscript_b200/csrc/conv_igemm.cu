@@ -85,7 +85,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
   const uint32_t stage_bytes = kABytes + ((b_bytes + 1023u) & ~1023u);
-  const uint32_t slab_base = smem_base + (uint32_t)p.stages * stage_bytes;
+  const uint32_t slab_base = smem_base + (uint32_t)(p.stages * p.ks) * stage_bytes;
   const uint32_t bar_base = slab_base + (uint32_t)p.nslab * kSlabBytes;
   // barriers: full[s], empty[s], tmem_full[2], tmem_empty[2], slab res_full / ready / free [nslab];
   // then the TMEM base address slot
@@ -145,11 +145,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // with warp-uniform values; one elected lane issues the copies)
     int s = 0;
     uint32_t ph = 0;
+    const int n_stages = p.stages, cin_chunks = p.cin_chunks, kw = p.kw, dil = p.dil, block_n = p.block_n;
+    const int ks = p.ks, n_groups = (k_iters + ks - 1) / ks;
+    const bool im2col = p.im2col != 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.n_blocks;
       const int mt = tile / p.n_blocks;
       int ix0, iy0, in0;
-      if (p.im2col) {
+      if (im2col) {
         // column = 128 consecutive output pixels in (n, oy, ox) order
         const int m0 = mt * 128;
         if (m0 >= m_valid) continue;
@@ -167,27 +170,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         iy0 = thi * p.th * p.sy - p.pad_y;
         in0 = tni * p.tn;
       }
-      int kcol = 0;
-      for (int ky = 0; ky < p.kh; ++ky) {
-        for (int kx = 0; kx < p.kw; ++kx) {
-          for (int cc = 0; cc < p.cin_chunks; ++cc) {
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            if (elect_one()) {
-              const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
-              mbar_expect_tx(full_bar(s), a_tx + b_bytes);
-              if (p.im2col)
-                tma_load_im2col_4d(a_dst, &tmA, full_bar(s), cc * 64, ix0, iy0, in0,
-                                   (uint16_t)(kx * p.dil), (uint16_t)(ky * p.dil));
-              else
-                tma_load_4d(a_dst, &tmA, full_bar(s), cc * 64, ix0 + kx * p.dil, iy0 + ky * p.dil,
-                            in0);
-              tma_load_2d(a_dst + kABytes, &tmB, full_bar(s), kcol, n_blk * p.block_n);
-            }
-            __syncwarp();
-            kcol += 64;
-            if (++s == p.stages) { s = 0; ph ^= 1u; }
+      // flat k loop over stage groups of ks 64-channel chunks (one barrier pair per group): (ky, kx, cc)
+      // advance incrementally; the loop-invariant launch parameters live in registers
+      const int b_row = n_blk * block_n;
+      int cc = 0, kx = 0, ky = 0, kcol = 0;
+      for (int g = 0; g < n_groups; ++g) {
+        mbar_wait(bar_base + 8u * (uint32_t)(n_stages + s), ph ^ 1u);           // empty[s]
+        const int nsub = (ks == 2 && g * 2 + 1 < k_iters) ? 2 : 1;
+        // coordinates of the (up to) two chunks of this group, computed by the whole warp
+        const int c0 = cc * 64, ox0 = kx * dil, oy0 = ky * dil, kc0 = kcol;
+        if (++cc == cin_chunks) { cc = 0; if (++kx == kw) { kx = 0; ++ky; } }
+        kcol += 64;
+        const int c1 = cc * 64, ox1 = kx * dil, oy1 = ky * dil, kc1 = kcol;
+        if (nsub == 2) {
+          if (++cc == cin_chunks) { cc = 0; if (++kx == kw) { kx = 0; ++ky; } }
+          kcol += 64;
+        }
+        if (elect_one()) {
+          const uint32_t a_dst = smem_base + (uint32_t)(s * ks) * stage_bytes;
+          const uint32_t fb = bar_base + 8u * (uint32_t)s;                        // full[s]
+          mbar_expect_tx(fb, (uint32_t)nsub * (a_tx + b_bytes));
+          if (im2col) tma_load_im2col_4d(a_dst, &tmA, fb, c0, ix0, iy0, in0, (uint16_t)ox0, (uint16_t)oy0);
+          else tma_load_4d(a_dst, &tmA, fb, c0, ix0 + ox0, iy0 + oy0, in0);
+          tma_load_2d(a_dst + kABytes, &tmB, fb, kc0, b_row);
+          if (nsub == 2) {
+            if (im2col) tma_load_im2col_4d(a_dst + stage_bytes, &tmA, fb, c1, ix0, iy0, in0, (uint16_t)ox1, (uint16_t)oy1);
+            else tma_load_4d(a_dst + stage_bytes, &tmA, fb, c1, ix0 + ox1, iy0 + oy1, in0);
+            tma_load_2d(a_dst + stage_bytes + kABytes, &tmB, fb, kc1, b_row);
           }
         }
+        __syncwarp();
+        if (++s == n_stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -199,6 +212,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t ph = 0;
     int as = 0;
     uint32_t aph = 0;
+    const int n_stages = p.stages, ks = p.ks, n_groups = (k_iters + ks - 1) / ks;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_blocks;
       if (p.im2col) {
@@ -209,22 +223,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(tempty_bar(as), aph ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_stride);
-      for (int it = 0; it < k_iters; ++it) {
+      for (int g = 0; g < n_groups; ++g) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
+        const int nsub = (ks == 2 && g * 2 + 1 < k_iters) ? 2 : 1;
         if (elect_one()) {
-          // descriptor low word = 16-byte-unit address | LBO: stepping a stage or a K=16 slice is an add
-          const uint32_t a_lo = desc_lo0 + (uint32_t)s * (stage_bytes >> 4);
-          const uint32_t b_lo = a_lo + (kABytes >> 4);
+          // descriptor low word = 16-byte-unit address | LBO: stepping a chunk or a K=16 slice is an add
+          uint32_t a_lo = desc_lo0 + (uint32_t)(s * ks) * (stage_bytes >> 4);
+          for (int j = 0; j < nsub; ++j) {
+            const uint32_t b_lo = a_lo + (kABytes >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16(d_tmem, ((uint64_t)kDescHi << 32) | (a_lo + 2u * k), ((uint64_t)kDescHi << 32) | (b_lo + 2u * k),
-                      idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(d_tmem, ((uint64_t)kDescHi << 32) | (a_lo + 2u * k), ((uint64_t)kDescHi << 32) | (b_lo + 2u * k),
+                        idesc, (g > 0 || j > 0 || k > 0) ? 1u : 0u);
+            }
+            a_lo += stage_bytes >> 4;
           }
-          umma_commit(empty_bar(s));  // frees the smem slot when these MMAs retire
+          umma_commit(empty_bar(s));  // frees the group's smem when these MMAs retire
         }
         __syncwarp();
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        if (++s == n_stages) { s = 0; ph ^= 1u; }
       }
       if (elect_one()) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
       __syncwarp();
@@ -662,18 +680,26 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
 
   const int b_bytes = (block_n * 128 + 1023) & ~1023;
   const int stage_bytes = kABytes + b_bytes;
+  // Narrow N tiles do little tensor work per 64-channel chunk (2*N clocks), less than one trip of the producer /
+  // MMA-issuer loops costs: group two chunks behind one barrier pair so the per-trip overhead is paid half as often.
+  // (only when at least three such groups fit beside the epilogue slabs: with two the producer cannot run ahead)
   const int fixed_bytes = 1024 /*align slack*/ + p.nslab * kSlabBytes + 8 * (2 * 8 + 4 + 3 * p.nslab) + 16;
+  int ks = (block_n <= 128 && k_iters >= 2 && (227 * 1024 - fixed_bytes) / (2 * stage_bytes) >= 3) ? 2 : 1;
+  if (d.ks == 1 || d.ks == 2) ks = d.ks;
+  if (ks == 2 && k_iters < 2) ks = 1;
+  p.ks = ks;
+  const int n_groups = (k_iters + ks - 1) / ks;
   int stages = d.stages;
   if (stages == 0) {
-    stages = (227 * 1024 - fixed_bytes) / stage_bytes;
+    stages = (227 * 1024 - fixed_bytes) / (ks * stage_bytes);
     if (stages > 8) stages = 8;
-    if (stages > k_iters + 1) stages = k_iters + 1;
+    if (stages > n_groups + 1) stages = n_groups + 1;
     if (stages < 2) stages = 2;
   }
   p.stages = stages;
-  plan->smem = stages * stage_bytes + p.nslab * kSlabBytes + 1024 /*align slack*/ +
+  plan->smem = stages * ks * stage_bytes + p.nslab * kSlabBytes + 1024 /*align slack*/ +
                8 * (2 * stages + 4 + 3 * p.nslab) + 16;
-  if (plan->smem > 227 * 1024) { set_error("conv: %d B of shared memory needed (block_n %d, stages %d, slabs %d)", plan->smem, block_n, stages, p.nslab); return -1; }
+  if (plan->smem > 227 * 1024) { set_error("conv: %d B of shared memory needed (block_n %d, stages %d x %d chunks, slabs %d)", plan->smem, block_n, stages, ks, p.nslab); return -1; }
 
   // A: 4-D (C, W, H, N) view of the input; box = (64 ch, tw, th, tn) output pixels, traversal
   // strides implement the convolution stride.

@@ -35,6 +35,7 @@ struct ConvDesc {
   int im2col = 1;                                 // A operand through im2col-mode TMA (else tiled boxes)
   int block_n = 0;                                // 0 = choose
   int stages = 0;                                 // 0 = choose
+  int ks = 0;                                     // 64-channel chunks per pipeline stage: 0 = choose, 1 or 2
 };
 
 struct ConvKParams {
@@ -44,6 +45,7 @@ struct ConvKParams {
   int H_out, W_out, N;
   int kh, kw, sx, sy, pad_x, pad_y, dil;
   int cin_chunks, stages, acc_stride;
+  int ks;                                         // 64-channel K chunks per stage group (one barrier pair each)
   int nslab, res_tma;                             // staged epilogue: slab ring size, residual through TMA
   int relu, out_fp32, res_shift, im2col;
   const float* bias;

@@ -61,6 +61,7 @@ typedef struct dpb200_conv2d_args {
   int64_t y_sc;             /* output channel stride in elements (0 or 1 = NHWC; >1 = channel-planar, fp32 only) */
   int32_t epilogue;         /* 0 automatic; 1 direct global stores; 2 shared-memory slabs + TMA store (bf16
                                [M,C] outputs; the residual is then prefetched by TMA too)            */
+  int32_t ks;               /* 64-channel K chunks per pipeline stage: 0 automatic (2 for N tiles <= 128), 1, 2 */
 } dpb200_conv2d_args;
 
 int dpb200_conv2d(const dpb200_conv2d_args* a, void* stream);

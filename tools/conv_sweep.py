@@ -46,33 +46,34 @@ def main():
         out = torch.empty(n, ho, wo, packed.shape[0], device="cuda", dtype=torch.bfloat16)
         flops = 2.0 * n * ho * wo * cout * cin * k * k
         by = x.numel() * 2 + out.numel() * 2 + packed.numel() * 2 + (res.numel() * 2 if has_res else 0)
-        cfgs = [(0, 0)]
+        cfgs = [(0, 0, 0)]
         for bn in (64, 128, 256):
             if bn <= packed.shape[0] and packed.shape[0] % bn == 0:
-                for st in (0, 2, 3, 4, 6, 8):
-                    cfgs.append((bn, st))
+                for ks in (1, 2):
+                    for st in (0, 2, 3, 4, 6):
+                        cfgs.append((bn, st, ks))
         best = None
-        for bn, st in cfgs:
+        for bn, st, ks in cfgs:
             ts = []
             try:
                 for _ in range(9):
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
                     ops.conv2d(x, packed, bias, k, k, stride, pad, 1, True, res=res, out=out, block_n=bn, stages=st,
-                               tiled=a.tiled)
+                               tiled=a.tiled, ks=ks)
                     e1.record()
                     torch.cuda.synchronize()
                     ts.append(e0.elapsed_time(e1))
             except Exception as ex:  # noqa: BLE001
-                print(f"{name:32s} block_n {bn:3d} stages {st}  -> {str(ex)[:80]}")
+                print(f"{name:32s} block_n {bn:3d} stages {st} ks {ks}  -> {str(ex)[:80]}")
                 continue
             ts = sorted(ts[2:])
             ms = ts[len(ts) // 2]
             tag = ""
             if best is None or ms < best[0]:
-                best = (ms, bn, st)
-            print(f"{name:32s} block_n {bn:3d} stages {st}  {ms:8.4f} ms  {flops / ms / 1e9:8.1f} TFLOP/s  {by / ms / 1e6:8.1f} GB/s{tag}")
-        print(f"{name:32s} BEST block_n {best[1]} stages {best[2]} {best[0]:.4f} ms\n")
+                best = (ms, bn, st, ks)
+            print(f"{name:32s} block_n {bn:3d} stages {st} ks {ks}  {ms:8.4f} ms  {flops / ms / 1e9:8.1f} TFLOP/s  {by / ms / 1e6:8.1f} GB/s{tag}")
+        print(f"{name:32s} BEST block_n {best[1]} stages {best[2]} ks {best[3]} {best[0]:.4f} ms\n")
 
 
 if __name__ == "__main__":
