@@ -173,15 +173,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // flat k loop over stage groups of ks 64-channel chunks (one barrier pair per group): (ky, kx, cc)
       // advance incrementally; the loop-invariant launch parameters live in registers
       const int b_row = n_blk * block_n;
+      // deconv phases: block (py,px) = (n_blk >> 1, n_blk & 1) starts its 2x2 taps at (py,px) of the 3x3 footprint
+      const int pyo = p.phase_taps ? (n_blk >> 1) * dil : 0, pxo = p.phase_taps ? (n_blk & 1) * dil : 0;
       int cc = 0, kx = 0, ky = 0, kcol = 0;
       for (int g = 0; g < n_groups; ++g) {
         mbar_wait(bar_base + 8u * (uint32_t)(n_stages + s), ph ^ 1u);           // empty[s]
         const int nsub = (ks == 2 && g * 2 + 1 < k_iters) ? 2 : 1;
         // coordinates of the (up to) two chunks of this group, computed by the whole warp
-        const int c0 = cc * 64, ox0 = kx * dil, oy0 = ky * dil, kc0 = kcol;
+        const int c0 = cc * 64, ox0 = kx * dil + pxo, oy0 = ky * dil + pyo, kc0 = kcol;
         if (++cc == cin_chunks) { cc = 0; if (++kx == kw) { kx = 0; ++ky; } }
         kcol += 64;
-        const int c1 = cc * 64, ox1 = kx * dil, oy1 = ky * dil, kc1 = kcol;
+        const int c1 = cc * 64, ox1 = kx * dil + pxo, oy1 = ky * dil + pyo, kc1 = kcol;
         if (nsub == 2) {
           if (++cc == cin_chunks) { cc = 0; if (++kx == kw) { kx = 0; ++ky; } }
           kcol += 64;
@@ -628,6 +630,13 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
         if (d.cout_pad % b == 0) { block_n = b; break; }
     }
   }
+  if (d.phase_taps) {
+    if (d.cout_pad % 64 != 0 || d.kh != 2 || d.kw != 2 || d.pad_x != 1 || d.pad_y != 1 || d.sx != 1 || d.sy != 1) {
+      set_error("conv: phase_taps needs k=2, pad=1, stride 1 and cout_pad = 4 x (multiple of 16)");
+      return -1;
+    }
+    block_n = d.cout_pad / 4;
+  }
   if (block_n % 16 != 0 || block_n > 256 || d.cout_pad % block_n != 0) {
     set_error("conv: bad block_n %d for cout_pad %d", block_n, d.cout_pad);
     return -1;
@@ -650,6 +659,7 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
   p.H_out = d.H_out; p.W_out = d.W_out; p.N = d.N;
   p.kh = d.kh; p.kw = d.kw; p.sx = d.sx; p.sy = d.sy; p.pad_x = d.pad_x; p.pad_y = d.pad_y;
   p.dil = d.dil;
+  p.phase_taps = d.phase_taps;
   p.cin_chunks = d.cin_pad / 64;
   p.relu = d.relu; p.out_fp32 = d.out_fp32; p.res_shift = d.res_shift;
   p.bias = d.bias;

@@ -36,6 +36,10 @@ struct ConvDesc {
   int block_n = 0;                                // 0 = choose
   int stages = 0;                                 // 0 = choose
   int ks = 0;                                     // 64-channel chunks per pipeline stage: 0 = choose, 1 or 2
+  // ConvTranspose2d(k4,s2,p1) as ONE launch: the four output-parity phases are the four N blocks (block_n =
+  // cout_pad / 4); block (py,px) reads its 2x2 taps at window offsets (ky+py, kx+px) of a pad-1 3x3 footprint,
+  // so the four CTAs working on one pixel tile share the same input rows through L2.
+  int phase_taps = 0;
 };
 
 struct ConvKParams {
@@ -48,6 +52,7 @@ struct ConvKParams {
   int ks;                                         // 64-channel K chunks per stage group (one barrier pair each)
   int nslab, res_tma;                             // staged epilogue: slab ring size, residual through TMA
   int relu, out_fp32, res_shift, im2col;
+  int phase_taps;
   const float* bias;
   const __nv_bfloat16* res;
   long long res_sn, res_sy, res_sx;

@@ -111,6 +111,7 @@ struct Builder {
     long long out_sn = 0, out_sy = 0, out_sx = 0, out_sc = 0; long long out_off = 0;   // output view overrides
     int H_out = 0, W_out = 0;
     bool no_bias = false;
+    int phase_taps = 0;
   };
 
   // y must be allocated by the caller (so views / slices are possible)
@@ -144,6 +145,7 @@ struct Builder {
     d.out = y.fp32 ? (void*)(reinterpret_cast<float*>(y.p) + o.out_off)
                    : (void*)(reinterpret_cast<bf16*>(y.p) + o.out_off);
     d.n_valid = o.n_valid;
+    d.phase_taps = o.phase_taps;
     if (d.cout_pad > y.C && !o.out_sx) { fail = -12; set_error("conv %s: output has %d channels, weights %d", wname.c_str(), y.C, d.cout_pad); return; }
     const double fl = 2.0 * x.N * d.H_out * d.W_out * (double)w->cout_pad * d.kh * d.kw * w->cin_pad;
     s->flops += fl;
@@ -475,20 +477,20 @@ int build_plan(dpb200_session* s) {
   }
   b.tap("dp_head", head_out);
   // ---- a18 predictor: ConvTranspose2d(k4,s2,p1) as four 2x2 phase convs, then bilinear x2 -> NCHW fp32.
-  // Output pixel (2y+py, 2x+px) of the deconv only depends on phase (py,px): each phase GEMM writes its
-  // own channel-planar fp32 block low[r][py][px][c][P][P] (TMEM lane = pixel, so planar stores coalesce).
+  // Output pixel (2y+py, 2x+px) of the deconv only depends on phase (py,px): the phase GEMMs (the four N blocks
+  // of one launch) each write their own channel-planar fp32 block low[r][py][px][c][P][P] (TMEM lane = pixel,
+  // so planar stores coalesce).
   const int Cp = round_up(cfg.coarse_ch + 75, 16);
   const int S2 = 2 * P;
   T4 low = b.act(Rd, 4 * Cp, P, P, 1);      // [Rd][2][2][Cp][P][P]
   s->low = (float*)low.p; s->low_S = S2; s->low_C = Cp;
-  for (int py = 0; py < 2; ++py)
-    for (int px = 0; px < 2; ++px) {
-      Builder::ConvOpt o; o.k = 2; o.pad_y = py == 0 ? 1 : 0; o.pad_x = px == 0 ? 1 : 0; o.n_valid = nv;
-      o.H_out = P; o.W_out = P;
-      o.out_sx = 1; o.out_sy = P; o.out_sc = (long long)P * P; o.out_sn = 4LL * Cp * P * P;
-      o.out_off = (long long)(py * 2 + px) * Cp * P * P;
-      b.conv("roi_heads.densepose_predictor.phase" + std::to_string(py * 2 + px), head_out, low, o);
-    }
+  {
+    // one launch: N blocks = the four phases, each reading its own 2x2 taps of the pad-1 3x3 footprint
+    Builder::ConvOpt o; o.k = 2; o.pad = 1; o.phase_taps = 1; o.n_valid = nv;
+    o.H_out = P; o.W_out = P;
+    o.out_sx = 1; o.out_sy = P; o.out_sc = (long long)P * P; o.out_sn = 4LL * Cp * P * P;
+    b.conv("roi_heads.densepose_predictor.phases", head_out, low, o);
+  }
   b.tap_raw("dp_lowres", low.p, Rd, 4, Cp, P * P, 1);
   {
     dpb200_session* ss = s;

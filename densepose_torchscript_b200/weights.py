@@ -152,4 +152,8 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], spec: ModelSpec, device) -> Dic
             kxs = [3 - 2 * t for t in range(2)] if px == 0 else [2 - 2 * t for t in range(2)]
             sub = wt[:, :, kys, :][:, :, :, kxs]                                 # [ci, co, ty, tx]
             out[pp + f"phase{py * 2 + px}"] = _pack_khwc(sub.permute(1, 2, 3, 0), bt, device)
+    # the four phases stacked on Cout: one GEMM launch whose N blocks are the phases (conv_igemm phase_taps)
+    ph = [out.pop(pp + f"phase{i}") for i in range(4)]
+    out[pp + "phases"] = (torch.cat([q[0] for q in ph], 0).contiguous(), torch.cat([q[1] for q in ph], 0).contiguous(),
+                          ph[0][2], 4 * ph[0][3])
     return out

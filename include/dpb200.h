@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DPB200_ABI_VERSION 2
+#define DPB200_ABI_VERSION 3
 
 const char* dpb200_last_error(void);
 int dpb200_abi_version(void);
@@ -33,8 +33,9 @@ int dpb200_device_ok(void);
  * Replaces F.conv2d in Conv2d.forward (detectron2/layers/wrappers.py:104-112) with FrozenBN
  * (detectron2/layers/batch_norm.py:54-62) pre-folded into w/bias, nn.Linear in
  * FastRCNNConvFCHead.forward (detectron2/modeling/roi_heads/box_head.py:95-98) and
- * FastRCNNOutputLayers.forward (fast_rcnn.py:238-257), and one output-parity phase of
- * ConvTranspose2d(k=4,s=2,p=1) in DensePoseChartPredictor (densepose/modeling/predictors/chart.py:45-59).
+ * FastRCNNOutputLayers.forward (fast_rcnn.py:238-257), and the four output-parity phases of
+ * ConvTranspose2d(k=4,s=2,p=1) in DensePoseChartPredictor (densepose/modeling/predictors/chart.py:45-59),
+ * one at a time or all four as the N blocks of one launch (phase_taps).
  *
  *   y[n,oy,ox,co] = act( sum x[n, oy*sy+ky*dil-pad_y, ox*sx+kx*dil-pad_x, ci] * w[co,(ky*kw+kx)*cin_pad+ci]
  *                        + bias[co] + res[n, oy>>res_shift, ox>>res_shift, co] )
@@ -62,6 +63,10 @@ typedef struct dpb200_conv2d_args {
   int32_t epilogue;         /* 0 automatic; 1 direct global stores; 2 shared-memory slabs + TMA store (bf16
                                [M,C] outputs; the residual is then prefetched by TMA too)            */
   int32_t ks;               /* 64-channel K chunks per pipeline stage: 0 automatic (2 for N tiles <= 128), 1, 2 */
+  int32_t phase_taps;       /* 1: the whole ConvTranspose2d(k=4,s=2,p=1) in one launch. wgt = the four phase
+                               matrices (py,px) stacked on cout ([4*c][4*cin_pad], kh=kw=2, pad 1, stride 1);
+                               N block (py,px) reads taps (ky+py, kx+px) of the pad-1 3x3 footprint and writes
+                               channels [(2*py+px)*c, +c) of y (h_out = h, w_out = w).                    */
 } dpb200_conv2d_args;
 
 int dpb200_conv2d(const dpb200_conv2d_args* a, void* stream);

@@ -68,6 +68,35 @@ def test_conv_igemm_matches_oracle(ops, case, tiled):
     assert rel_l2(got, bf16(ref)) < 3e-3
 
 
+@pytest.mark.parametrize("tiled", [False, True])
+def test_deconv_four_phases_in_one_launch(ops, tiled):
+    """ConvTranspose2d(k=4,s=2,p=1) (chart.py:45-59) as one GEMM launch whose N blocks are the output-parity phases."""
+    from densepose_torchscript_b200.weights import _pack_khwc
+    g = torch.Generator().manual_seed(11)
+    R, P, Cin, Cout = 5, 14, 128, 77
+    x = bf16(torch.randn(R, Cin, P, P, generator=g))
+    wt = bf16(torch.randn(Cin, Cout, 4, 4, generator=g) / math.sqrt(Cin * 4))
+    bt = torch.randn(Cout, generator=g)
+    ref = F.conv_transpose2d(x, wt, bt, stride=2, padding=1)                   # [R, Cout, 2P, 2P]
+    ph = []
+    for py in range(2):
+        for px in range(2):
+            kys = [3 - 2 * t for t in range(2)] if py == 0 else [2 - 2 * t for t in range(2)]
+            kxs = [3 - 2 * t for t in range(2)] if px == 0 else [2 - 2 * t for t in range(2)]
+            ph.append(_pack_khwc(wt[:, :, kys, :][:, :, :, kxs].permute(1, 2, 3, 0), bt, "cuda"))
+    packed = torch.cat([q[0] for q in ph], 0).contiguous()
+    bias = torch.cat([q[1] for q in ph], 0).contiguous()
+    cp = ph[0][3]
+    nv = torch.tensor([4], dtype=torch.int32, device="cuda")
+    out = torch.full((R, 4 * cp, P, P), -3.0, device="cuda")
+    ops.conv2d(nhwc_bf16_cuda(x), packed, bias, 2, 2, pad=1, planar=True, out=out, phase_taps=True, tiled=tiled, n_valid=nv)
+    torch.cuda.synchronize()
+    low = out.view(R, 2, 2, cp, P, P)[:, :, :, :Cout].cpu()                  # [r, py, px, c, y, x]
+    got = low.permute(0, 3, 4, 1, 5, 2).reshape(R, Cout, 2 * P, 2 * P)          # (2y+py, 2x+px)
+    assert float((got[:4] - ref[:4]).abs().max()) < 2e-4                        # fp32 accumulate, fp32 store
+    assert bool((out[4:] == -3.0).all())
+
+
 def test_conv_fp32_out_and_n_valid(ops):
     g = torch.Generator().manual_seed(5)
     x = bf16(torch.randn(9, 256, 28, 28, generator=g))

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(_lib.lib, name), f"{name} is declared in dpb200.h but not exported by libdpb200.so"
     assert declared == set(_lib.EXPORTS)
-    assert _lib.lib.dpb200_abi_version() == 2
+    assert _lib.lib.dpb200_abi_version() == 3
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     for name in declared:
         assert re.search(rf"\bT {name}\b", out), name
@@ -128,9 +128,12 @@ def test_pack_special_layouts_are_exact_relayouts():
     bt = torch.cat([sd[f"roi_heads.densepose_predictor.{n}.bias"] for n in names], 0)
     ref = F.conv_transpose2d(x, wt, bt, stride=2, padding=1)
     out = torch.zeros_like(ref)
+    pall = packed["roi_heads.densepose_predictor.phases"]          # the four phases stacked on Cout
+    assert pall[0].shape == (320, 4 * 512) and pall[3] == 320 and pall[1].shape == (320,)
     for py in range(2):
         for px in range(2):
-            pk = packed[f"roi_heads.densepose_predictor.phase{py * 2 + px}"]
+            i = py * 2 + px
+            pk = (pall[0][80 * i:80 * i + 80], pall[1][80 * i:80 * i + 80], pall[2], 80)
             w = _unpack(pk, 2, 2, 512, 77)
             xp = F.pad(x, (1 if px == 0 else 0, 0 if px == 0 else 1, 1 if py == 0 else 0, 0 if py == 0 else 1))
             out[:, :, py::2, px::2] = F.conv2d(xp, w, pk[1][:77])
