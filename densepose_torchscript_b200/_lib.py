@@ -39,7 +39,7 @@ class Conv2dArgs(C.Structure):
         ("res", vp), ("res_sn", i64), ("res_sy", i64), ("res_sx", i64), ("res_shift", i32),
         ("y", vp), ("y_fp32", i32), ("y_sn", i64), ("y_sy", i64), ("y_sx", i64),
         ("n_valid", vp), ("block_n", i32), ("stages", i32), ("tiled", i32),
-        ("y_sc", i64), ("epilogue", i32), ("ks", i32), ("phase_taps", i32),
+        ("y_sc", i64), ("epilogue", i32), ("ks", i32), ("phase_taps", i32), ("pair", i32),
     ]
 
 

@@ -48,7 +48,7 @@ int dpb200_conv2d(const dpb200_conv2d_args* a, void* stream) {
   d.out_sx = a->y_sx ? a->y_sx : a->cout_pad;
   d.out_sy = a->y_sy ? a->y_sy : d.out_sx * a->w_out;
   d.out_sn = a->y_sn ? a->y_sn : d.out_sy * a->h_out;
-  d.n_valid = a->n_valid; d.block_n = a->block_n; d.stages = a->stages; d.ks = a->ks; d.phase_taps = a->phase_taps;
+  d.n_valid = a->n_valid; d.block_n = a->block_n; d.stages = a->stages; d.ks = a->ks; d.phase_taps = a->phase_taps; d.pair = a->pair;
   d.im2col = a->tiled ? 0 : 1;
   d.out_sc = a->y_sc > 0 ? a->y_sc : 1;
   d.epilogue = a->epilogue;

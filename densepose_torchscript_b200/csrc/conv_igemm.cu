@@ -15,6 +15,7 @@
 //   warp 2        : TMEM alloc / dealloc  warps 4..7    : epilogue (TMEM lane quarter = warp % 4)
 #include "conv_igemm.cuh"
 #include "ptx.cuh"
+#include "device_utils.cuh"
 
 #include <stdarg.h>
 #include <stdio.h>
@@ -71,7 +72,14 @@ __device__ __forceinline__ void epi_slab_half(const uint32_t* v, const float4* b
 // kStaged: bf16 NHWC outputs leave through shared-memory slabs and TMA stores (and the residual arrives by
 // TMA into the same slab), so the epilogue warps only touch TMEM and shared memory. Otherwise every
 // epilogue thread stores its own row straight to global memory (fp32 / strided / planar outputs).
-template <bool kStaged>
+//
+// kPair (staged, im2col only): two CTAs of a cluster work as one cta_group::2 MMA unit on a 256-row x block_n tile.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (block_n/2 weight rows), so the pair reads the
+// weights from L2 once instead of twice; the leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 for both,
+// every CTA drains its own TMEM lanes (its 128 output rows). full[] lives in the leader (both CTAs' TMA loads
+// count their bytes there), empty[] / tmem_full[] are signalled in both CTAs by multicast commits, and the leader's
+// tmem_empty[] collects one arrive per epilogue warp of both CTAs.
+template <bool kStaged, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -83,7 +91,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   // 1024-byte aligned stage buffers (SWIZZLE_128B atoms are 8 rows x 128 B)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const uint32_t b_bytes = (uint32_t)(kPair ? p.block_n >> 1 : p.block_n) * 128u;
   const uint32_t stage_bytes = kABytes + ((b_bytes + 1023u) & ~1023u);
   const uint32_t slab_base = smem_base + (uint32_t)(p.stages * p.ks) * stage_bytes;
   const uint32_t bar_base = slab_base + (uint32_t)p.nslab * kSlabBytes;
@@ -117,7 +126,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpiThreads);
+      mbar_init(tempty_bar(s), kPair ? 2 * (kEpiThreads / 32) : kEpiThreads);
     }
     for (int s = 0; s < p.nslab; ++s) {
       mbar_init(sres_bar(s), 1);
@@ -126,15 +135,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
-  tc_fence_before();
-  __syncthreads();
+  if (kPair) {
+    cluster_sync_divergent();                       // both CTAs' barriers exist before anything remote can touch them
+    if (warp == 2) tmem_alloc_pair(tmem_slot, tmem_cols);
+    tc_fence_before();
+    cluster_sync_divergent();
+  } else {
+    if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int nvalid = p.n_valid ? min(*p.n_valid, p.N) : p.N;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total_tiles = m_tiles * p.n_blocks;
+  // pair mode: a "tile" is a pair of consecutive 128-row tiles (this CTA takes the rank-th of them)
+  const int total_tiles = (kPair ? (m_tiles + 1) >> 1 : m_tiles) * p.n_blocks;
+  const int t_begin = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int k_iters = p.kh * p.kw * p.cin_chunks;
   const uint32_t a_tx = p.im2col ? (uint32_t)kABytes : (uint32_t)(p.tw * p.th * p.tn) * 128u;
   const int hw_out = p.H_out * p.W_out;
@@ -148,14 +167,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int n_stages = p.stages, cin_chunks = p.cin_chunks, kw = p.kw, dil = p.dil, block_n = p.block_n;
     const int ks = p.ks, n_groups = (k_iters + ks - 1) / ks;
     const bool im2col = p.im2col != 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = t_begin; tile < total_tiles; tile += t_step) {
       const int n_blk = tile % p.n_blocks;
-      const int mt = tile / p.n_blocks;
+      int mt = tile / p.n_blocks;
+      if (kPair) {
+        if (mt * 256 >= m_valid) continue;
+        mt = 2 * mt + (int)rank;
+      }
       int ix0, iy0, in0;
       if (im2col) {
         // column = 128 consecutive output pixels in (n, oy, ox) order
         const int m0 = mt * 128;
-        if (m0 >= m_valid) continue;
+        if (!kPair && m0 >= m_valid) continue;
         in0 = m0 / hw_out;
         const int rem = m0 - in0 * hw_out;
         const int oy0 = rem / p.W_out;
@@ -172,7 +195,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       // flat k loop over stage groups of ks 64-channel chunks (one barrier pair per group): (ky, kx, cc)
       // advance incrementally; the loop-invariant launch parameters live in registers
-      const int b_row = n_blk * block_n;
+      const int b_row = n_blk * block_n + (kPair ? (int)rank * (block_n >> 1) : 0);
       // deconv phases: block (py,px) = (n_blk >> 1, n_blk & 1) starts its 2x2 taps at (py,px) of the 3x3 footprint
       const int pyo = p.phase_taps ? (n_blk >> 1) * dil : 0, pxo = p.phase_taps ? (n_blk & 1) * dil : 0;
       int cc = 0, kx = 0, ky = 0, kcol = 0;
@@ -188,7 +211,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (++cc == cin_chunks) { cc = 0; if (++kx == kw) { kx = 0; ++ky; } }
           kcol += 64;
         }
-        if (elect_one()) {
+        if (kPair) {
+          if (elect_one()) {
+            const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
+            const uint32_t fb = bar_base + 8u * (uint32_t)s;                      // full[s]
+            if (rank == 0) mbar_expect_tx(fb, 2u * (a_tx + b_bytes));             // both CTAs' bytes land here
+            const uint32_t fb0 = mapa_shared(fb, 0);
+            tma_load_im2col_4d_pair(a_dst, &tmA, fb0, c0, ix0, iy0, in0, (uint16_t)ox0, (uint16_t)oy0);
+            tma_load_2d_pair(a_dst + kABytes, &tmB, fb0, kc0, b_row);
+          }
+        } else if (elect_one()) {
           const uint32_t a_dst = smem_base + (uint32_t)(s * ks) * stage_bytes;
           const uint32_t fb = bar_base + 8u * (uint32_t)s;                        // full[s]
           mbar_expect_tx(fb, (uint32_t)nsub * (a_tx + b_bytes));
@@ -205,9 +237,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (++s == n_stages) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane)
-    const uint32_t idesc = umma_idesc_bf16(128, p.block_n);
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane;
+    // pair mode: the leader CTA only)
+    const uint32_t idesc = umma_idesc_bf16(kPair ? 256 : 128, p.block_n);
     const uint32_t desc_lo0 = (uint32_t)(umma_desc_sw128(smem_base) & 0xffffffffu);
     constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO | version | SWIZZLE_128B
     int s = 0;
@@ -215,9 +248,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int as = 0;
     uint32_t aph = 0;
     const int n_stages = p.stages, ks = p.ks, n_groups = (k_iters + ks - 1) / ks;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = t_begin; tile < total_tiles; tile += t_step) {
       const int mt = tile / p.n_blocks;
-      if (p.im2col) {
+      if (kPair) {
+        if (mt * 256 >= m_valid) continue;
+      } else if (p.im2col) {
         if (mt * 128 >= m_valid) continue;
       } else {
         if ((mt / (p.tiles_w * p.tiles_h)) * p.tn >= nvalid) continue;
@@ -236,17 +271,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t b_lo = a_lo + (kABytes >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              umma_bf16(d_tmem, ((uint64_t)kDescHi << 32) | (a_lo + 2u * k), ((uint64_t)kDescHi << 32) | (b_lo + 2u * k),
-                        idesc, (g > 0 || j > 0 || k > 0) ? 1u : 0u);
+              if (kPair)
+                umma_bf16_pair(d_tmem, ((uint64_t)kDescHi << 32) | (a_lo + 2u * k), ((uint64_t)kDescHi << 32) | (b_lo + 2u * k),
+                               idesc, (g > 0 || j > 0 || k > 0) ? 1u : 0u);
+              else
+                umma_bf16(d_tmem, ((uint64_t)kDescHi << 32) | (a_lo + 2u * k), ((uint64_t)kDescHi << 32) | (b_lo + 2u * k),
+                          idesc, (g > 0 || j > 0 || k > 0) ? 1u : 0u);
             }
             a_lo += stage_bytes >> 4;
           }
-          umma_commit(empty_bar(s));  // frees the group's smem when these MMAs retire
+          // frees the group's smem (in both CTAs of a pair) when these MMAs retire
+          if (kPair) umma_commit_pair(empty_bar(s));
+          else umma_commit(empty_bar(s));
         }
         __syncwarp();
         if (++s == n_stages) { s = 0; ph ^= 1u; }
       }
-      if (elect_one()) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+      if (elect_one()) {                             // accumulator complete -> epilogue (of both CTAs)
+        if (kPair) umma_commit_pair(tfull_bar(as));
+        else umma_commit(tfull_bar(as));
+      }
       __syncwarp();
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
@@ -255,11 +299,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int slabs_per_tile = p.block_n >> 6;
     int slot = 0;
     uint32_t sph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = t_begin; tile < total_tiles; tile += t_step) {
       const int n_blk = tile % p.n_blocks;
-      const int mt = tile / p.n_blocks;
+      int mt = tile / p.n_blocks;
+      if (kPair) {
+        if (mt * 256 >= m_valid) continue;
+        mt = 2 * mt + (int)rank;
+      }
       const int m0 = mt * 128;
-      if (m0 >= m_valid) continue;
+      if (!kPair && m0 >= m_valid) continue;
       for (int j = 0; j < slabs_per_tile; ++j) {
         mbar_wait(sfree_bar(slot), sph ^ 1u);
         mbar_expect_tx(sres_bar(slot), (uint32_t)kSlabBytes);
@@ -273,14 +321,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int slabs_per_tile = p.block_n >> 6;
     int slot = 0, prev = -1;
     uint32_t sph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = t_begin; tile < total_tiles; tile += t_step) {
       const int n_blk = tile % p.n_blocks;
-      const int mt = tile / p.n_blocks;
+      int mt = tile / p.n_blocks;
+      if (kPair) {
+        if (mt * 256 >= m_valid) continue;
+        mt = 2 * mt + (int)rank;
+      }
       const int m0 = mt * 128;
-      if (m0 >= m_valid) continue;
+      if (!kPair && m0 >= m_valid) continue;
       for (int j = 0; j < slabs_per_tile; ++j) {
         mbar_wait(sready_bar(slot), sph);
-        tma_store_2d(&tmOut, slab_base + (uint32_t)slot * kSlabBytes, n_blk * p.block_n + j * 64, m0);
+        // (pair mode: the second CTA's tile can lie wholly past the valid rows; it still runs the barrier protocol)
+        if (!kPair || m0 < m_valid)
+          tma_store_2d(&tmOut, slab_base + (uint32_t)slot * kSlabBytes, n_blk * p.block_n + j * 64, m0);
         tma_store_commit();
         if (prev >= 0) {
           tma_store_wait_read<1>();     // every store but the one just issued has drained its slab
@@ -309,11 +363,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool has_res = p.res != nullptr;
     int as = 0, slot = 0;
     uint32_t aph = 0, sph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = t_begin; tile < total_tiles; tile += t_step) {
       const int n_blk = tile % p.n_blocks;
-      const int mt = tile / p.n_blocks;
+      int mt = tile / p.n_blocks;
+      if (kPair) {
+        if (mt * 256 >= m_valid) continue;
+        mt = 2 * mt + (int)rank;
+      }
       const int m0 = mt * 128;
-      if (m0 >= m_valid) continue;
+      if (!kPair && m0 >= m_valid) continue;
       const int c_base = n_blk * p.block_n + hh * 32;
       uint32_t res_off = 0;                       // element offset of this row's residual pixel (gathered mode)
       if (has_res && !p.res_tma) {               // top-down add (res_shift) or an irregular residual view
@@ -387,7 +445,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (++slot == p.nslab) { slot = 0; sph ^= 1u; }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(as));
+      if (kPair) {                                  // one arrive per warp on the LEADER's barrier
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0));
+      } else {
+        mbar_arrive(tempty_bar(as));
+      }
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
   } else if (!kStaged && warp >= 4) {
@@ -402,7 +465,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int rn = p.im2col ? 0 : row / (p.tw * p.th);
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = t_begin; tile < total_tiles; tile += t_step) {
       const int n_blk = tile % p.n_blocks;
       const int mt = tile / p.n_blocks;
       int ox, oy, on;
@@ -499,10 +562,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (kPair) cluster_sync_divergent();             // the peer's shared memory / TMEM / barriers stay alive until both are done
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if (kPair) tmem_dealloc_pair(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -688,7 +754,15 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
   p.nslab = 0;
   if (staged) p.nslab = (p.res_tma && k_iters <= 2) ? 8 : (k_iters > 16 ? 2 : 4);
 
-  const int b_bytes = (block_n * 128 + 1023) & ~1023;
+  // CTA pairs (cta_group::2): staged im2col convs whose N tile splits into two halves of a multiple of 16 rows.
+  // Chosen automatically for the long-K, 256-wide tiles (the 3x3 256->256 / 512->512 convs), where halving the
+  // weight traffic from L2 pays; d.pair forces it on (2) or off (1).
+  const bool pair_ok = staged && d.im2col && block_n % 32 == 0 && block_n >= 64 && (num_sms & ~1) >= 2;
+  if (d.pair == 2 && !pair_ok) { set_error("conv: pair mode needs a staged im2col conv with block_n %% 32 == 0"); return -1; }
+  const bool pair = d.pair == 2 || (d.pair == 0 && pair_ok && block_n == 256 && k_iters >= 18 && m_total >= 256LL * num_sms);
+  plan->pair = pair ? 1 : 0;
+  const int b_rows = pair ? block_n / 2 : block_n;
+  const int b_bytes = (b_rows * 128 + 1023) & ~1023;
   const int stage_bytes = kABytes + b_bytes;
   // Narrow N tiles do little tensor work per 64-channel chunk (2*N clocks), less than one trip of the producer /
   // MMA-issuer loops costs: group two chunks behind one barrier pair so the per-trip overhead is paid half as often.
@@ -697,6 +771,7 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
   int ks = (block_n <= 128 && k_iters >= 2 && (227 * 1024 - fixed_bytes) / (2 * stage_bytes) >= 3) ? 2 : 1;
   if (d.ks == 1 || d.ks == 2) ks = d.ks;
   if (ks == 2 && k_iters < 2) ks = 1;
+  if (pair) ks = 1;
   p.ks = ks;
   const int n_groups = (k_iters + ks - 1) / ks;
   int stages = d.stages;
@@ -738,7 +813,7 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
     const uint64_t K = (uint64_t)d.kh * d.kw * d.cin_pad;
     uint64_t dims[2] = {K, (uint64_t)d.cout_pad};
     uint64_t strides[1] = {K * 2};
-    uint32_t box[2] = {64, (uint32_t)block_n};
+    uint32_t box[2] = {64, (uint32_t)b_rows};
     uint32_t estr[2] = {1, 1};
     int r = encode_tiled_bf16(&plan->tmB, d.w, 2, dims, strides, box, estr);
     if (r) return r;
@@ -764,15 +839,23 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
   const long long total_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
   plan->grid = (int)(total_tiles < num_sms ? total_tiles : num_sms);
   if (plan->grid < 1) plan->grid = 1;
+  if (pair) {
+    const long long pair_tiles = (((long long)p.tiles_w + 1) / 2) * p.n_blocks;
+    const long long ctas = 2 * pair_tiles;
+    plan->grid = (int)(ctas < (num_sms & ~1) ? ctas : (num_sms & ~1));
+  }
   plan->flops = 2.0 * d.N * d.H_out * d.W_out * (double)d.cout_pad * d.kh * d.kw * d.Cin;
   return 0;
 }
 
 int conv_kernels_init() {
-  cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false>,
+  cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(conv_igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              227 * 1024);
   if (e != cudaSuccess) { set_error("conv: smem attr: %s", cudaGetErrorString(e)); return -3; }
   return 0;
@@ -786,12 +869,26 @@ int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
     if (conv_kernels_init()) return -3;
     init_dev = dev;
   }
-  if (plan.staged)
-    conv_igemm_kernel<true><<<plan.grid, kThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.tmOut,
-                                                                        plan.tmRes, plan.p);
+  if (plan.pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)plan.grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)plan.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, true>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes,
+                                        plan.p);
+    if (le != cudaSuccess) { set_error("conv pair launch: %s", cudaGetErrorString(le)); return -4; }
+  } else if (plan.staged)
+    conv_igemm_kernel<true, false><<<plan.grid, kThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.tmOut,
+                                                                               plan.tmRes, plan.p);
   else
-    conv_igemm_kernel<false><<<plan.grid, kThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.tmOut,
-                                                                         plan.tmRes, plan.p);
+    conv_igemm_kernel<false, false><<<plan.grid, kThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.tmOut,
+                                                                                plan.tmRes, plan.p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv launch: %s", cudaGetErrorString(e)); return -4; }
   return 0;

@@ -40,6 +40,7 @@ struct ConvDesc {
   // cout_pad / 4); block (py,px) reads its 2x2 taps at window offsets (ky+py, kx+px) of a pad-1 3x3 footprint,
   // so the four CTAs working on one pixel tile share the same input rows through L2.
   int phase_taps = 0;
+  int pair = 0;                                   // CTA pairs (cta_group::2, weights split over the pair): 0 choose, 1 off, 2 on
 };
 
 struct ConvKParams {
@@ -67,6 +68,7 @@ struct ConvPlan {
   alignas(64) CUtensorMap tmOut;   // staged epilogue: [M, cout] bf16 view of the output
   alignas(64) CUtensorMap tmRes;   // staged epilogue: [M, cout] bf16 view of the residual
   int staged = 0;
+  int pair = 0;                    // launched as clusters of two CTAs (cta_group::2)
   ConvKParams p;
   int grid = 0;
   int smem = 0;

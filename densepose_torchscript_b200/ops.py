@@ -46,7 +46,7 @@ def conv2d(x: torch.Tensor, packed: torch.Tensor, bias: Optional[torch.Tensor], 
            res: Optional[torch.Tensor] = None, res_shift: int = 0, out_fp32: bool = False,
            n_valid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
            block_n: int = 0, stages: int = 0, tiled: bool = False, epilogue: int = 0,
-           planar: bool = False, ks: int = 0, phase_taps: bool = False) -> torch.Tensor:
+           planar: bool = False, ks: int = 0, phase_taps: bool = False, pair: int = 0) -> torch.Tensor:
     """x: bf16 NHWC [N,H,W,Cin] (contiguous). Returns NHWC [N,Ho,Wo,cout_pad] bf16 (or fp32); with
     planar=True the fp32 result is channel-planar [N,cout_pad,Ho,Wo]."""
     _lib.require_device()
@@ -83,6 +83,7 @@ def conv2d(x: torch.Tensor, packed: torch.Tensor, bias: Optional[torch.Tensor], 
     a.n_valid = _p(n_valid)
     a.block_n, a.stages, a.tiled, a.ks = block_n, stages, int(tiled), ks
     a.phase_taps = int(phase_taps)
+    a.pair = pair
     check(lib.dpb200_conv2d(C.byref(a), _stream()), "dpb200_conv2d")
     return out
 

@@ -67,6 +67,9 @@ typedef struct dpb200_conv2d_args {
                                matrices (py,px) stacked on cout ([4*c][4*cin_pad], kh=kw=2, pad 1, stride 1);
                                N block (py,px) reads taps (ky+py, kx+px) of the pad-1 3x3 footprint and writes
                                channels [(2*py+px)*c, +c) of y (h_out = h, w_out = w).                    */
+  int32_t pair;             /* CTA pairs: clusters of two CTAs run one tcgen05.mma.cta_group::2 on a 256-row tile,
+                               each CTA staging half of the weight tile. 0 automatic (long-K 256-wide tiles), 1 off,
+                               2 on (needs the slab epilogue, tiled == 0 and an N tile that is a multiple of 32) */
 } dpb200_conv2d_args;
 
 int dpb200_conv2d(const dpb200_conv2d_args* a, void* stream);

@@ -68,6 +68,58 @@ def test_conv_igemm_matches_oracle(ops, case, tiled):
     assert rel_l2(got, bf16(ref)) < 3e-3
 
 
+PAIR_CASES = [
+    # N, H, W, Cin, Cout, k, pad, dil, relu, res(0 none,1 same,2 up2), block_n, n_valid
+    (6, 28, 28, 128, 512, 3, 1, 1, True, 0, 256, 0),       # head-conv shape, 37 tiles (odd: last pair half empty)
+    (6, 28, 28, 128, 512, 3, 1, 1, True, 0, 256, 3),       # device-side count: tiles past the valid rows
+    (2, 50, 84, 256, 256, 3, 1, 1, False, 0, 256, 0),      # FPN output / RPN conv shape
+    (2, 25, 42, 64, 256, 1, 0, 1, True, 1, 256, 0),        # residual through TMA
+    (1, 50, 84, 128, 256, 1, 0, 1, False, 2, 128, 0),      # gathered top-down residual, two N blocks of 128
+    (3, 28, 28, 256, 64, 3, 6, 6, False, 0, 64, 0),        # dilated, narrow tile
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_cta_pairs_match_single_cta_bitwise(ops, case):
+    """cta_group::2 launch (clusters of two CTAs, weights split over the pair) == the single-CTA kernel, bit for bit,
+    and both within tolerance of F.conv2d."""
+    N, H, W, Cin, Cout, k, pad, dil, relu, res_mode, block_n, n_valid = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = bf16(torch.randn(N, Cin, H, W, generator=g))
+    w = bf16(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k))
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x, w, b, padding=pad, dilation=dil)
+    res = None
+    if res_mode == 1:
+        res = bf16(torch.randn_like(ref))
+        ref = ref + res
+    elif res_mode == 2:
+        res = bf16(torch.randn(N, Cout, (H + 1) // 2, (W + 1) // 2, generator=g))
+        ref = ref + F.interpolate(res, scale_factor=2.0, mode="nearest")[:, :, :H, :W]
+    if relu:
+        ref = F.relu(ref)
+    packed, bias, _, cout_pad = ops.pack_conv_weight(w.cuda(), b.cuda())
+    nv = torch.tensor([n_valid], dtype=torch.int32, device="cuda") if n_valid else None
+    outs = []
+    for pair in (1, 2):
+        out = torch.full((N, H, W, cout_pad), -5.0, device="cuda", dtype=torch.bfloat16)
+        ops.conv2d(nhwc_bf16_cuda(x), packed, bias, k, k, pad=pad, dil=dil, relu=relu,
+                   res=None if res is None else nhwc_bf16_cuda(res), res_shift=1 if res_mode == 2 else 0,
+                   block_n=block_n, epilogue=2, pair=pair, n_valid=nv, out=out)
+        torch.cuda.synchronize()
+        outs.append(out)
+    nvis = n_valid if n_valid else N
+    assert torch.equal(outs[0][:nvis], outs[1][:nvis])
+    got = nchw(outs[1][:nvis, ..., :Cout])
+    tol = float(ref.abs().max()) * 2.0 ** -8 + 1e-3
+    assert float((got - ref[:nvis]).abs().max()) <= tol
+    if n_valid:
+        # rows of images past the count may be touched only inside the last (partial) 256-row pair tile
+        flat = outs[1].view(-1, cout_pad)
+        first_free = ((n_valid * H * W + 255) // 256) * 256
+        assert bool((flat[first_free:] == -5.0).all())
+
+
 @pytest.mark.parametrize("tiled", [False, True])
 def test_deconv_four_phases_in_one_launch(ops, tiled):
     """ConvTranspose2d(k=4,s=2,p=1) (chart.py:45-59) as one GEMM launch whose N blocks are the output-parity phases."""
