@@ -88,6 +88,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // warp index made provably warp-uniform, so the role loops below compile to uniform-datapath code
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  griddep_launch_dependents();      // the next kernel may start its own prologue as soon as SMs free up
 
   // 1024-byte aligned stage buffers (SWIZZLE_128B atoms are 8 rows x 128 B)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -147,6 +148,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlaps the tail of the
+  // previous kernel in the stream; its results (and n_valid) are only touched after this wait.
+  griddep_wait();
 
   const int nvalid = p.n_valid ? min(*p.n_valid, p.N) : p.N;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -759,7 +763,8 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
   // weight traffic from L2 pays; d.pair forces it on (2) or off (1).
   const bool pair_ok = staged && d.im2col && block_n % 32 == 0 && block_n >= 64 && (num_sms & ~1) >= 2;
   if (d.pair == 2 && !pair_ok) { set_error("conv: pair mode needs a staged im2col conv with block_n %% 32 == 0"); return -1; }
-  const bool pair = d.pair == 2 || (d.pair == 0 && pair_ok && block_n == 256 && k_iters >= 18 && m_total >= 256LL * num_sms);
+  // (measured on the path's shapes: short-K tiles lose to the pair's extra barrier traffic; K >= 18 chunks gains 6-10 %)
+  const bool pair = d.pair == 2 || (d.pair == 0 && pair_ok && block_n == 256 && k_iters >= 18 && m_total >= 4096);
   plan->pair = pair ? 1 : 0;
   const int b_rows = pair ? block_n / 2 : block_n;
   const int b_bytes = (b_rows * 128 + 1023) & ~1023;
@@ -869,26 +874,32 @@ int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
     if (conv_kernels_init()) return -3;
     init_dev = dev;
   }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)plan.grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = (size_t)plan.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  // programmatic dependent launch (the kernel calls griddepcontrol.wait before it reads anything)
+  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
   if (plan.pair) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)plan.grid);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = (size_t)plan.smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, true>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes,
-                                        plan.p);
-    if (le != cudaSuccess) { set_error("conv pair launch: %s", cudaGetErrorString(le)); return -4; }
-  } else if (plan.staged)
-    conv_igemm_kernel<true, false><<<plan.grid, kThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.tmOut,
-                                                                               plan.tmRes, plan.p);
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)na;
+  cudaError_t le;
+  if (plan.pair)
+    le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, true>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.p);
+  else if (plan.staged)
+    le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, false>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.p);
   else
-    conv_igemm_kernel<false, false><<<plan.grid, kThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.tmOut,
-                                                                                plan.tmRes, plan.p);
+    le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, false>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.p);
+  if (le != cudaSuccess) { set_error("conv launch: %s", cudaGetErrorString(le)); return -4; }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv launch: %s", cudaGetErrorString(e)); return -4; }
   return 0;
