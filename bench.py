@@ -140,6 +140,8 @@ def ncu_conv_traffic_gb():
         return None, None
     rows = list(csv.reader(open(p)))
     h = rows[0]
+    if "dram__bytes_read.sum" not in h:
+        return None, None
     ir, iw, io = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("op")
     ur, uw = rows[1][ir], rows[1][iw]
     scale = {"Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0, "byte": 1e-9}
@@ -324,11 +326,16 @@ def run_ours(a):
         return out
 
     pcie = pcie_probe()
-    ms_e2e, h2d, d2h = measure_e2e(False)
-    ms_e2e_x, h2d_x, d2h_x, dets_x = measure_e2e_extracted()
-    # the same with the DensePose tensors produced as fp16 by the kernel (what the reference's `.half()` module,
-    # run.py's GPU default, returns): half the D2H bytes
-    ms_e2e_half, _, d2h_half = measure_e2e(True)
+    if a.no_e2e:        # sweeps over large batches (tools/sweep.sh): only the device-resident number
+        ms_e2e = ms_e2e_x = ms_e2e_half = float("nan")
+        h2d = d2h = h2d_x = d2h_x = d2h_half = 0
+        dets_x = 0.0
+    else:
+        ms_e2e, h2d, d2h = measure_e2e(False)
+        ms_e2e_x, h2d_x, d2h_x, dets_x = measure_e2e_extracted()
+        # the same with the DensePose tensors produced as fp16 by the kernel (what the reference's `.half()` module,
+        # run.py's GPU default, returns): half the D2H bytes
+        ms_e2e_half, _, d2h_half = measure_e2e(True)
 
     # ---- p50 batch-1 latency (BASELINE.json's second metric): one image, host in -> host out, synchronous
     lat = None
@@ -460,6 +467,9 @@ def run_ours(a):
         line["hbm_kernels"] = [{"kernel": n, "launches": c, "ms": round(ms, 4), "algorithmic_gb": round(by / 1e9, 4),
                                 "achieved_gbs": round(by / 1e6 / ms, 1), "frac_of_measured_hbm": round(by / 1e6 / ms / peak_hbm, 3)}
                                for n, (ms, by, c) in sorted(agg.items(), key=lambda t: -t[1][0])]
+        if a.no_e2e:
+            for k in ("e2e", "e2e_half_outputs", "e2e_extracted"):
+                line.pop(k)
         if lat is not None:
             line["latency_batch1"] = lat
         if world == 1 and not a.no_cpu_baseline:
@@ -484,6 +494,7 @@ def main():
     ap.add_argument("--width", type=int, default=1333)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-in/host-out pipelines (batch sweeps)")
     ap.add_argument("--profile-out", default="", help="write the per-launch ms profile (JSON) here")
     a = ap.parse_args()
     if a.impl == "reference":
