@@ -41,23 +41,26 @@ __device__ __forceinline__ Tap make_tap(float v, int size) {
 }
 
 // acc += ((w1*v1 + w2*v2) + w3*v3) + w4*v4 for one bf16 pair of each of the four taps; every product and
-// sum individually rounded (torchvision's CPU kernel has no FMA contraction). Products are scalar mul.rn
-// (never contracted); the sums are packed add.rn.f32x2. (ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into
-// FFMA2 despite the explicit rounding modifiers, so the products must not be packed.)
-__device__ __forceinline__ uint64_t prod2(float w, uint32_t q) {
-  return pack_f32x2(__float_as_uint(__fmul_rn(w, __uint_as_float(q << 16))),
-                    __float_as_uint(__fmul_rn(w, __uint_as_float(q & 0xffff0000u))));
+// sum individually rounded (torchvision's CPU kernel has no FMA contraction). Two channels per instruction:
+// the products are mul.rn.f32x2 and every sum is fma.rn.f32x2(p, ONE, s) = round(p * 1 + s) = round(p + s).
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 despite the rounding modifiers; it cannot
+// contract into an FMA whose multiplier is a run-time value, so ONE = (1.0f, 1.0f) arrives as a kernel
+// argument and the SASS is FMUL2 + FFMA2(p, 1.0, s): bit-identical to separately rounded scalar code.
+__device__ __forceinline__ uint64_t prod2(uint64_t w, uint32_t q) {
+  return mul_f32x2(w, pack_f32x2(q << 16, q & 0xffff0000u));
 }
 __device__ __forceinline__ uint64_t tap_accum(uint64_t acc, uint32_t q1, uint32_t q2, uint32_t q3, uint32_t q4,
-                                              float w1, float w2, float w3, float w4) {
-  const uint64_t sum = add_f32x2(add_f32x2(add_f32x2(prod2(w1, q1), prod2(w2, q2)), prod2(w3, q3)), prod2(w4, q4));
-  return add_f32x2(acc, sum);
+                                              uint64_t w1, uint64_t w2, uint64_t w3, uint64_t w4, uint64_t one) {
+  uint64_t sum = fma_f32x2(prod2(w2, q2), one, prod2(w1, q1));
+  sum = fma_f32x2(prod2(w3, q3), one, sum);
+  sum = fma_f32x2(prod2(w4, q4), one, sum);
+  return fma_f32x2(sum, one, acc);
 }
 
 // One block per ROI. The 2P sample coordinates per axis are resolved once into shared-memory tap tables;
 // then a group of C/8 threads (16 bytes of channels each) walks the bins: 16 independent 16-byte loads in
 // flight per thread, packed f32x2 arithmetic, one 16-byte store.
-__global__ void __launch_bounds__(256) roi_align_kernel(RoiAlignArgs a) {
+__global__ void __launch_bounds__(256) roi_align_kernel(RoiAlignArgs a, float one_f) {
   __shared__ Tap s_ty[64], s_tx[64];
   const int r = blockIdx.x;
   if (a.n_rois != nullptr && r >= *a.n_rois) return;
@@ -102,6 +105,7 @@ __global__ void __launch_bounds__(256) roi_align_kernel(RoiAlignArgs a) {
   const int chunk = threadIdx.x % C8;
   const int group = threadIdx.x / C8, groups = blockDim.x / C8;
   const uint4* fc = feat + chunk;
+  const uint64_t one = pack_f32x2(__float_as_uint(one_f), __float_as_uint(one_f));
   for (int bin = group; bin < P * P; bin += groups) {
     const int ph = bin / P, pw = bin - ph * P;
     uint64_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;    // four (+0, +0) pairs = 8 channels
@@ -112,16 +116,18 @@ __global__ void __launch_bounds__(256) roi_align_kernel(RoiAlignArgs a) {
       for (int ix = 0; ix < 2; ++ix) {
         const Tap tx = s_tx[2 * pw + ix];
         if (ty.lo < 0 || tx.lo < 0) continue;
-        const float w1 = __fmul_rn(ty.h, tx.h), w2 = __fmul_rn(ty.h, tx.l);
-        const float w3 = __fmul_rn(ty.l, tx.h), w4 = __fmul_rn(ty.l, tx.l);
+        const float f1 = __fmul_rn(ty.h, tx.h), f2 = __fmul_rn(ty.h, tx.l);
+        const float f3 = __fmul_rn(ty.l, tx.h), f4 = __fmul_rn(ty.l, tx.l);
+        const uint64_t w1 = pack_f32x2(__float_as_uint(f1), __float_as_uint(f1)), w2 = pack_f32x2(__float_as_uint(f2), __float_as_uint(f2));
+        const uint64_t w3 = pack_f32x2(__float_as_uint(f3), __float_as_uint(f3)), w4 = pack_f32x2(__float_as_uint(f4), __float_as_uint(f4));
         const uint4 q1 = __ldg(fc + (ty.lo * W + tx.lo) * C8);
         const uint4 q2 = __ldg(fc + (ty.lo * W + tx.hi) * C8);
         const uint4 q3 = __ldg(fc + (ty.hi * W + tx.lo) * C8);
         const uint4 q4 = __ldg(fc + (ty.hi * W + tx.hi) * C8);
-        acc0 = tap_accum(acc0, q1.x, q2.x, q3.x, q4.x, w1, w2, w3, w4);
-        acc1 = tap_accum(acc1, q1.y, q2.y, q3.y, q4.y, w1, w2, w3, w4);
-        acc2 = tap_accum(acc2, q1.z, q2.z, q3.z, q4.z, w1, w2, w3, w4);
-        acc3 = tap_accum(acc3, q1.w, q2.w, q3.w, q4.w, w1, w2, w3, w4);
+        acc0 = tap_accum(acc0, q1.x, q2.x, q3.x, q4.x, w1, w2, w3, w4, one);
+        acc1 = tap_accum(acc1, q1.y, q2.y, q3.y, q4.y, w1, w2, w3, w4, one);
+        acc2 = tap_accum(acc2, q1.z, q2.z, q3.z, q4.z, w1, w2, w3, w4, one);
+        acc3 = tap_accum(acc3, q1.w, q2.w, q3.w, q4.w, w1, w2, w3, w4, one);
       }
     }
     // / count (= 4): a power of two, so the multiply is the exactly rounded quotient as well
@@ -144,7 +150,7 @@ int launch_roi_align(const RoiAlignArgs& a, cudaStream_t s) {
   if (a.C % 8 || 256 % (a.C / 8)) { set_error("roi_align: C/8 must divide 256"); return -1; }
   if (a.P > 32) { set_error("roi_align: pooler resolution %d > 32", a.P); return -1; }
   if (a.R == 0) return 0;
-  roi_align_kernel<<<a.R, 256, 0, s>>>(a);
+  roi_align_kernel<<<a.R, 256, 0, s>>>(a, 1.0f);   // 1.0f as a run-time value: see tap_accum
   DPB_CHECK_LAUNCH("roi_align");
   return 0;
 }
