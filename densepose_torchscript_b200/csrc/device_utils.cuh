@@ -71,6 +71,11 @@ __device__ __forceinline__ uint32_t cluster_map_shared(uint32_t saddr, uint32_t 
 __device__ __forceinline__ void st_shared_cluster_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ double ld_shared_cluster_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
 // all threads of all CTAs of the cluster; release/acquire orders shared::cluster and global accesses
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -3,6 +3,7 @@
 #include "kernels.cuh"
 #include "conv_igemm.cuh"
 #include "ptx.cuh"
+#include "device_utils.cuh"
 
 #include <cuda_fp16.h>
 
@@ -267,11 +268,22 @@ groupnorm_relu_kernel(const uint4* __restrict__ x, const float* __restrict__ gam
   const int pstart = threadIdx.x / C8;
   const int pstep = blockDim.x / C8;
   float sum = 0.f, sq = 0.f;
-  for (int p = pstart; p < HW; p += pstep) {
-    float f[8];
-    unpack8(__ldg(xr + (long long)p * C8 + chunk), f);
+  // four independent 16-byte loads in flight per thread (a plain loop issues load -> use -> load: one ROI pass is
+  // then bound by HBM latency, not bandwidth); missing tail pixels read as zeros, which add nothing
+  for (int p = pstart; p < HW; p += 4 * pstep) {
+    uint4 v[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { sum += f[i]; sq += f[i] * f[i]; }
+    for (int j = 0; j < 4; ++j) {
+      const int q = p + j * pstep;
+      v[j] = q < HW ? __ldg(xr + (long long)q * C8 + chunk) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+      unpack8(v[j], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sum += f[i]; sq += f[i] * f[i]; }
+    }
   }
   const int grp = (chunk * 8) / cpg;
   atomicAdd(&s_sum[grp], (double)sum);
@@ -291,12 +303,23 @@ groupnorm_relu_kernel(const uint4* __restrict__ x, const float* __restrict__ gam
   for (int i = 0; i < 8; ++i) { g[i] = gamma[chunk * 8 + i]; bt[i] = beta[chunk * 8 + i]; }
   const float mean = s_mean[grp], rstd = s_rstd[grp];
   if (out_hw == HW) {
-    for (int p = pstart; p < HW; p += pstep) {
-      float f[8];
-      unpack8(__ldg(xr + (long long)p * C8 + chunk), f);
+    for (int p = pstart; p < HW; p += 4 * pstep) {
+      uint4 v[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaxf((f[i] - mean) * rstd * g[i] + bt[i], 0.f);
-      *reinterpret_cast<uint4*>(y + ((long long)r * out_hw + p) * y_cstride + chunk * 8) = pack8(f);
+      for (int j = 0; j < 4; ++j) {
+        const int q = p + j * pstep;
+        v[j] = q < HW ? __ldg(xr + (long long)q * C8 + chunk) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = p + j * pstep;
+        if (q >= HW) break;
+        float f[8];
+        unpack8(v[j], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fmaxf((f[i] - mean) * rstd * g[i] + bt[i], 0.f);
+        *reinterpret_cast<uint4*>(y + ((long long)r * out_hw + q) * y_cstride + chunk * 8) = pack8(f);
+      }
     }
   } else {
     // HW == 1: normalise the single pixel and broadcast it (bilinear from 1x1 is a broadcast)
@@ -310,12 +333,99 @@ groupnorm_relu_kernel(const uint4* __restrict__ x, const float* __restrict__ gam
   }
 }
 
+// Single-HBM-pass variant for the 28x28 ROI tensors: GroupNorm groups are independent, so one CTA takes one ROI and a
+// 64-channel slice (4 or 8 whole groups; 128-byte rows = full cache lines), keeps its 784 x 128 B = 98 KB in shared
+// memory, reduces the group statistics locally (fixed order: deterministic) and writes the normalised slice: one read
+// and one write of the tensor instead of two reads (with hundreds of ROIs in flight the second read misses L2) and one
+// write. Two CTAs share an SM, so one's loads overlap the other's stores.
+static constexpr int kGnSliceC = 64;
+__global__ void __launch_bounds__(512, 2)
+groupnorm_relu_slice_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                            bf16* __restrict__ y, int HW, int C, int y_cstride, const int* __restrict__ n_valid) {
+  extern __shared__ __align__(16) uint4 gn_tile[];            // [HW][8] uint4
+  __shared__ double s_part[16][8][2];                         // per warp, per 8-channel chunk: sum, sum of squares
+  __shared__ float s_mean[8], s_rstd[8];                      // per chunk (chunks of one group hold the same values)
+  const int slices = C / kGnSliceC;
+  const int r = blockIdx.x / slices, sl = blockIdx.x - r * slices;
+  if (n_valid != nullptr && r >= *n_valid) return;
+  const int C8 = C / 8, cpg = C / 32;
+  const int chunk = threadIdx.x & 7;                          // 16-byte chunk (8 channels) of the slice
+  const int prow = threadIdx.x >> 3;                          // 64 pixel rows per pass
+  const uint4* xr = x + (long long)r * HW * C8 + sl * 8 + chunk;
+  float sum = 0.f, sq = 0.f;
+  for (int p = prow; p < HW; p += 4 * 64) {
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = p + j * 64;
+      v[j] = q < HW ? __ldg(xr + (long long)q * C8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = p + j * 64;
+      if (q < HW) gn_tile[q * 8 + chunk] = v[j];
+      float f[8];
+      unpack8(v[j], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sum += f[i]; sq += f[i] * f[i]; }
+    }
+  }
+  // lanes l, l+8, l+16, l+24 of a warp hold the same chunk: fold them, then one fp64 partial per (warp, chunk)
+  sum += __shfl_xor_sync(0xffffffffu, sum, 8);  sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 16); sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 8) { s_part[warp][lane][0] = (double)sum; s_part[warp][lane][1] = (double)sq; }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    // group of this chunk: cpg/8 consecutive chunks (1 chunk when C = 256, 2 when C = 512)
+    const int cpc = cpg / 8;                                  // chunks per group
+    const int c0 = (threadIdx.x / cpc) * cpc;
+    double ts = 0.0, tq = 0.0;
+    for (int c = c0; c < c0 + cpc; ++c)
+      for (int w = 0; w < 16; ++w) { ts += s_part[w][c][0]; tq += s_part[w][c][1]; }
+    const double n = (double)HW * cpg;
+    const double m = ts / n;
+    double var = tq / n - m * m;
+    if (var < 0) var = 0;
+    s_mean[threadIdx.x] = (float)m;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  float g[8], bt[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { g[i] = gamma[sl * kGnSliceC + chunk * 8 + i]; bt[i] = beta[sl * kGnSliceC + chunk * 8 + i]; }
+  const float mean = s_mean[chunk], rstd = s_rstd[chunk];
+  bf16* yr = y + (long long)r * HW * y_cstride + sl * kGnSliceC + chunk * 8;
+  for (int p = prow; p < HW; p += 64) {
+    float f[8];
+    unpack8(gn_tile[p * 8 + chunk], f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaxf((f[i] - mean) * rstd * g[i] + bt[i], 0.f);
+    *reinterpret_cast<uint4*>(yr + (long long)p * y_cstride) = pack8(f);
+  }
+}
+
 int launch_groupnorm_relu(const bf16* x, const float* gamma, const float* beta, bf16* y, int R, int HW,
                           int C, int y_cstride, int out_hw, const int* n_valid, cudaStream_t s) {
   if (C % 256 != 0 || C > 512 * 8 || (out_hw != HW && HW != 1)) { set_error("groupnorm: bad shape"); return -1; }
   const int C8 = C / 8;
   int threads = 512;
   if (threads % C8) { set_error("groupnorm: C/8 must divide 512"); return -1; }
+  if (out_hw == HW && C % kGnSliceC == 0 && (C / 32) % 8 == 0 && HW * 128 <= 100 * 1024 && R > 0) {
+    const int smem = HW * 128;
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !done[dev]) {
+      if (cudaFuncSetAttribute(groupnorm_relu_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) !=
+          cudaSuccess) { set_error("groupnorm: smem attribute"); return -3; }
+      done[dev] = true;
+    }
+    groupnorm_relu_slice_kernel<<<R * (C / kGnSliceC), 512, smem, s>>>(reinterpret_cast<const uint4*>(x), gamma, beta, y, HW,
+                                                                      C, y_cstride, n_valid);
+    DPB_CHECK_LAUNCH("groupnorm_relu_slice");
+    return 0;
+  }
   groupnorm_relu_kernel<<<R, threads, 0, s>>>(reinterpret_cast<const uint4*>(x), gamma, beta, y, HW, C,
                                               y_cstride, out_hw, n_valid);
   DPB_CHECK_LAUNCH("groupnorm_relu");

@@ -214,13 +214,16 @@ def box_predict(head: torch.Tensor, prop_boxes: torch.Tensor, prop_count: torch.
     return raw, boxes, scores, count
 
 
-def groupnorm_relu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_hw: Optional[int] = None) -> torch.Tensor:
-    """x [R,HW,C] bf16 -> [R,out_hw,C] bf16."""
+def groupnorm_relu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_hw: Optional[int] = None,
+                   out: Optional[torch.Tensor] = None, n_valid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [R,HW,C] bf16 -> [R,out_hw,C] bf16. `out` may be a channel slice of a wider [R,out_hw,Ctot] tensor (the ASPP
+    concat, deeplab.py:141); `n_valid` a device int32 count of the ROIs actually present."""
     r, hw, c = x.shape
     out_hw = hw if out_hw is None else out_hw
-    y = torch.empty(r, out_hw, c, dtype=torch.bfloat16, device=x.device)
-    check(lib.dpb200_groupnorm_relu(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), r, hw, c, c, out_hw,
-                                    None, _stream()), "dpb200_groupnorm_relu")
+    y = torch.empty(r, out_hw, c, dtype=torch.bfloat16, device=x.device) if out is None else out
+    assert y.dtype == torch.bfloat16 and y.stride(2) == 1 and y.stride(0) == out_hw * y.stride(1)
+    check(lib.dpb200_groupnorm_relu(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), r, hw, c, y.stride(1),
+                                    out_hw, _p(n_valid), _stream()), "dpb200_groupnorm_relu")
     return y
 
 

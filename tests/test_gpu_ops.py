@@ -426,6 +426,29 @@ def test_groupnorm_relu(ops, C):
     assert rel_l2(got, ref) < 3e-3 and frac_equal(got, ref) > 0.97
 
 
+def test_groupnorm_relu_into_concat_slice_with_count(ops):
+    """The ASPP branches write their normalised output straight into a channel slice of the 1280-channel concat
+    (deeplab.py:141); ROIs past the device-side count stay untouched; two runs are bit-identical."""
+    g = torch.Generator().manual_seed(9)
+    R, C = 7, 256
+    x = bf16(torch.randn(R, C, 28, 28, generator=g) * 1.5 - 0.2)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    ref = bf16(F.relu(F.group_norm(x, 32, gamma, beta, eps=1e-5)))
+    xin = x.permute(0, 2, 3, 1).reshape(R, 784, C).contiguous().to(torch.bfloat16).cuda()
+    nv = torch.tensor([5], dtype=torch.int32, device="cuda")
+    outs = []
+    for _ in range(2):
+        cat = torch.full((R, 784, 1280), -2.0, dtype=torch.bfloat16, device="cuda")
+        ops.groupnorm_relu(xin, gamma.cuda(), beta.cuda(), out=cat[:, :, 512:768], n_valid=nv)
+        torch.cuda.synchronize()
+        outs.append(cat)
+    assert torch.equal(outs[0], outs[1])
+    cat = outs[0].float().cpu()
+    got = cat[:5, :, 512:768].reshape(5, 28, 28, C).permute(0, 3, 1, 2)
+    assert rel_l2(got, ref[:5]) < 3e-3 and frac_equal(got, ref[:5]) > 0.97
+    assert bool((cat[5:] == -2.0).all()) and bool((cat[:, :, :512] == -2.0).all()) and bool((cat[:, :, 768:] == -2.0).all())
+
+
 def test_avgpool_and_broadcast_gn(ops):
     g = torch.Generator().manual_seed(41)
     x = bf16(torch.randn(4, 256, 28, 28, generator=g))
