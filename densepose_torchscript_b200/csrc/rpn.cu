@@ -250,47 +250,82 @@ int launch_nms_sorted(const float* boxes, int n, float thr, unsigned char* keep,
 }
 
 // ---------------------------------------------------------------------------------------- merge
+// proposal_utils.py:118-126 after the per-level NMS: torchvision's batched_nms returns the kept candidates of all
+// levels sorted by score, keep[:post_topk]. Every level's candidate list is already sorted (score descending, ties by
+// ascending anchor index), so no sort is needed: the final rank of a kept candidate is the number of kept candidates
+// ahead of it = (kept ones before it in its own level) + per other level (kept ones among the first p entries, p found
+// by binary search on that level's sorted scores; equal scores: the lower level goes first, as the (score, ~index)
+// keys of the previous bitonic sort ordered them). One CTA per image, 1024 threads, ~5 k candidates.
 __global__ void __launch_bounds__(1024) rpn_merge_kernel(RpnArgs a) {
-  extern __shared__ unsigned long long mkeys[];   // 8192
-  __shared__ unsigned s_n;
-  const int b = blockIdx.x;
-  if (threadIdx.x == 0) s_n = 0;
-  for (int i = threadIdx.x; i < 8192; i += blockDim.x) mkeys[i] = 0ull;
-  __syncthreads();
-  const int total = 5 * a.pre_topk;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int lvl = i / a.pre_topk, t = i - lvl * a.pre_topk;
-    const long long slot = ((long long)b * 5 + lvl) * a.pre_topk + t;
-    if (t < a.cand_count[b * 5 + lvl] && a.cand_keep[slot]) {
-      // key 0 is reserved for "empty": ordered keys of finite floats are never 0
-      mkeys[i] = ((unsigned long long)f2ord(a.cand_scores[slot]) << 32) | (0xFFFFFFFFu - (uint32_t)i);
-      atomicAdd(&s_n, 1u);
+  __shared__ uint32_t s_ord[5][1024];       // order-preserving score keys, 0 = empty slot (sorts last)
+  __shared__ uint16_t s_pref[5][1024];      // exclusive prefix count of kept candidates
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_total[5];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  uint32_t flags = 0;                         // bit l: candidate (level l, position t) is kept
+  for (int l = 0; l < 5; ++l) {
+    const long long slot = ((long long)b * 5 + l) * a.pre_topk + t;
+    const bool valid = t < a.pre_topk && t < a.cand_count[b * 5 + l];
+    s_ord[l][t] = valid ? f2ord(a.cand_scores[slot]) : 0u;
+    const uint32_t k = (valid && a.cand_keep[slot]) ? 1u : 0u;
+    flags |= k << l;
+    // block-wide exclusive scan of k
+    uint32_t incl = k;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += v;
+      }
+      s_warp[lane] = w;
+      if (lane == 31) s_total[l] = w;
+    }
+    __syncthreads();
+    s_pref[l][t] = (uint16_t)(incl - k + (warp > 0 ? s_warp[warp - 1] : 0u));
+    __syncthreads();
+  }
+  for (int l = 0; l < 5; ++l) {
+    if (!((flags >> l) & 1u)) continue;
+    const uint32_t key = s_ord[l][t];
+    uint32_t rank = s_pref[l][t];
+    for (int m = 0; m < 5; ++m) {
+      if (m == l) continue;
+      // first position p of level m whose candidate does NOT come before (key, l): entries are descending
+      int lo = 0, hi = 1024;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const uint32_t o = s_ord[m][mid];
+        const bool before = o > key || (o == key && m < l);
+        if (before) lo = mid + 1; else hi = mid;
+      }
+      rank += lo < 1024 ? (uint32_t)s_pref[m][lo] : s_total[m];
+    }
+    if (rank < (uint32_t)a.post_topk) {
+      const long long slot = ((long long)b * 5 + l) * a.pre_topk + t;
+      reinterpret_cast<float4*>(a.prop_boxes)[(long long)b * a.post_topk + rank] = reinterpret_cast<const float4*>(a.cand_boxes)[slot];
+      a.prop_scores[(long long)b * a.post_topk + rank] = a.cand_scores[slot];
     }
   }
-  __syncthreads();
-  bitonic_sort_desc(mkeys, 8192);
-  const int n = (int)s_n < a.post_topk ? (int)s_n : a.post_topk;
-  for (int t = threadIdx.x; t < a.post_topk; t += blockDim.x) {
-    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-    float sc = 0.f;
-    if (t < n) {
-      const uint32_t i = 0xFFFFFFFFu - (uint32_t)(mkeys[t] & 0xFFFFFFFFull);
-      const int lvl = i / a.pre_topk, tt = i - lvl * a.pre_topk;
-      const long long slot = ((long long)b * 5 + lvl) * a.pre_topk + tt;
-      bx = reinterpret_cast<const float4*>(a.cand_boxes)[slot];
-      sc = a.cand_scores[slot];
-    }
-    reinterpret_cast<float4*>(a.prop_boxes)[(long long)b * a.post_topk + t] = bx;
-    a.prop_scores[(long long)b * a.post_topk + t] = sc;
+  const uint32_t kept = s_total[0] + s_total[1] + s_total[2] + s_total[3] + s_total[4];
+  const int n = (int)kept < a.post_topk ? (int)kept : a.post_topk;
+  for (int i = n + t; i < a.post_topk; i += blockDim.x) {
+    reinterpret_cast<float4*>(a.prop_boxes)[(long long)b * a.post_topk + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    a.prop_scores[(long long)b * a.post_topk + i] = 0.f;
   }
-  if (threadIdx.x == 0) a.prop_count[b] = n;
+  if (t == 0) a.prop_count[b] = n;
 }
 
 int launch_rpn_merge(const RpnArgs& a, cudaStream_t s) {
-  if (5 * a.pre_topk > 8192) { set_error("rpn_merge: too many candidates"); return -1; }
-  static bool done[64] = {};
-  if (ensure_smem((const void*)rpn_merge_kernel, 8192 * 8, done)) return -3;
-  rpn_merge_kernel<<<a.B, 1024, 8192 * 8, s>>>(a);
+  if (a.pre_topk > 1024) { set_error("rpn_merge: pre_topk > 1024"); return -1; }
+  rpn_merge_kernel<<<a.B, 1024, 0, s>>>(a);
   DPB_CHECK_LAUNCH("rpn_merge");
   return 0;
 }
