@@ -149,6 +149,28 @@ def ncu_conv_traffic_gb():
     return tot, "profiles/r01_ncu_step_sections.csv"
 
 
+def ncu_stage_limits():
+    """Per stage kernel, from the committed ncu capture of this workload: the SM / DRAM / L2 throughput percentages ncu
+    reports (which unit actually bounds a kernel whose HBM fraction is low)."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r01_ncu_step_sections.csv")
+    if not os.path.exists(p):
+        return {}
+    rows = list(csv.reader(open(p)))
+    h = rows[0]
+    need = {"sm_pct": "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+            "l2_pct": "lts__throughput.avg.pct_of_peak_sustained_elapsed"}
+    if any(v not in h for v in need.values()) or "op" not in h:
+        return {}
+    out = {}
+    for r in rows[2:]:
+        op = r[h.index("op")]
+        if op and not op.startswith("conv:") and op not in out:        # first launch of each stage kernel
+            out[op] = {k: round(float(r[h.index(v)]), 1) for k, v in need.items()}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def cpu_reference_rate(height, width, steps, warmup, config=CONFIG, max_seconds=120.0):
     """images/s of the reference's CPU path (oracle port, fp32, mode='ref') on this host."""
@@ -475,8 +497,11 @@ def run_ours(a):
             if not n.startswith("conv:") and by > 0:
                 a_ = agg.setdefault(n, [0.0, 0.0, 0])
                 a_[0] += ms; a_[1] += by; a_[2] += 1
-        line["hbm_kernels"] = [{"kernel": n, "launches": c, "ms": round(ms, 4), "algorithmic_gb": round(by / 1e9, 4),
-                                "achieved_gbs": round(by / 1e6 / ms, 1), "frac_of_measured_hbm": round(by / 1e6 / ms / peak_hbm, 3)}
+        limits = ncu_stage_limits()
+        line["hbm_kernels"] = [dict({"kernel": n, "launches": c, "ms": round(ms, 4), "algorithmic_gb": round(by / 1e9, 4),
+                                     "achieved_gbs": round(by / 1e6 / ms, 1),
+                                     "frac_of_measured_hbm": round(by / 1e6 / ms / peak_hbm, 3)},
+                                    **({"ncu": limits[n]} if n in limits else {}))
                                for n, (ms, by, c) in sorted(agg.items(), key=lambda t: -t[1][0])]
         if a.no_e2e:
             for k in ("e2e", "e2e_half_outputs", "e2e_extracted"):

@@ -225,3 +225,29 @@ def test_session_cache_is_bounded(s1x):
         assert r["image_size"].tolist() == [h, w]
         assert len(eng._sessions) <= 2
     assert (1, 64, 96, False, 0, False) in eng._sessions and (1, 80, 80, False, 0, False) in eng._sessions
+
+
+@pytest.mark.parametrize("name", ["densepose_rcnn_R_50_FPN_s1x", "densepose_rcnn_R_101_FPN_DL_s1x"])
+def test_no_detections_gives_correctly_shaped_empty_outputs(name):
+    """D = 0: with a score threshold nothing passes, every ROI-side kernel sees a device-side count of
+    zero (skipped tiles in the CTA-pair convs, the one-launch deconv, GroupNorm, the predictor tail) and the result
+    is the reference's empty dict; a following normal run on the same engine is unaffected."""
+    from dataclasses import replace
+
+    from densepose_torchscript_b200.config import BUILTIN
+    from densepose_torchscript_b200.engine import Engine
+    sd = W.make_state_dict(O.SPECS[name], 0)
+    spec = replace(BUILTIN[name], min_size=256, max_size=448)
+    imgs = torch.stack([W.synthetic_image(128, 192, seed=5), W.synthetic_image(128, 192, seed=6)])
+    none = Engine(replace(spec, score_thresh=0.99999), sd).forward_batch(imgs)
+    torch.cuda.synchronize()
+    for r in none:
+        assert r["pred_boxes"].shape == (0, 4) and r["scores"].shape == (0,) and r["pred_classes"].shape == (0,)
+        assert r["pred_densepose_coarse_segm"].shape == (0, spec.coarse_ch, 112, 112)
+        for k in DP[1:]:
+            assert r[k].shape == (0, 25, 112, 112)
+        assert r["image_size"].tolist() == [128, 192]
+    some = Engine(spec, sd).forward_batch(imgs)
+    torch.cuda.synchronize()
+    assert all(len(r["scores"]) > 0 for r in some)
+    assert all(bool(torch.isfinite(r["pred_densepose_u"]).all()) for r in some)
