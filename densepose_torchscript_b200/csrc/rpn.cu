@@ -70,12 +70,23 @@ rpn_topk_decode_kernel(RpnArgs a) {
     const int nb = 1 << bits[pass];
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int px = threadIdx.x; px < npix; px += blockDim.x) {
-      const float4 v = __ldg(head4 + (long long)px * 4);      // (logit a0, a1, a2, first delta): one 16-byte load
-      const uint32_t u0 = f2ord(v.x), u1 = f2ord(v.y), u2 = f2ord(v.z);
-      if ((u0 & mask) == prefix) atomicAdd(&hist[(u0 >> shifts[pass]) & (nb - 1)], 1u);
-      if ((u1 & mask) == prefix) atomicAdd(&hist[(u1 >> shifts[pass]) & (nb - 1)], 1u);
-      if ((u2 & mask) == prefix) atomicAdd(&hist[(u2 >> shifts[pass]) & (nb - 1)], 1u);
+    // one CTA streams a whole level (1 MB for p2): four independent 16-byte loads per thread are issued before any
+    // is used, otherwise every pass is a chain of dependent L2 round trips
+    for (int px0 = threadIdx.x; px0 < npix; px0 += 4 * blockDim.x) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int px = px0 + j * blockDim.x;
+        if (px < npix) v[j] = __ldg(head4 + (long long)px * 4);   // (logit a0, a1, a2, first delta): one 16-byte load
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (px0 + j * (int)blockDim.x >= npix) break;
+        const uint32_t u0 = f2ord(v[j].x), u1 = f2ord(v[j].y), u2 = f2ord(v[j].z);
+        if ((u0 & mask) == prefix) atomicAdd(&hist[(u0 >> shifts[pass]) & (nb - 1)], 1u);
+        if ((u1 & mask) == prefix) atomicAdd(&hist[(u1 >> shifts[pass]) & (nb - 1)], 1u);
+        if ((u2 & mask) == prefix) atomicAdd(&hist[(u2 >> shifts[pass]) & (nb - 1)], 1u);
+      }
     }
     __syncthreads();
     // reversed bins: thread t owns reversed positions 2t, 2t+1 (bin = nb-1-pos)
@@ -102,15 +113,25 @@ rpn_topk_decode_kernel(RpnArgs a) {
   keys[threadIdx.x] = 0ull;
   __syncthreads();
   const bool take_all_eq = (eq_total == remaining);
-  for (int px = threadIdx.x; px < npix; px += blockDim.x) {
-    const float4 v = __ldg(head4 + (long long)px * 4);
-    const uint32_t us[3] = {f2ord(v.x), f2ord(v.y), f2ord(v.z)};
+  for (int px0 = threadIdx.x; px0 < npix; px0 += 4 * blockDim.x) {
+    float4 v4[4];
 #pragma unroll
-    for (int an = 0; an < 3; ++an) {
-      const uint32_t u = us[an];
-      if (u > T || (take_all_eq && u == T)) {
-        const unsigned pos = atomicAdd(&s_cnt, 1u);
-        if (pos < 1024) keys[pos] = ((unsigned long long)u << 32) | (0xFFFFFFFFu - (uint32_t)(px * 3 + an));
+    for (int j = 0; j < 4; ++j) {
+      const int px = px0 + j * blockDim.x;
+      if (px < npix) v4[j] = __ldg(head4 + (long long)px * 4);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int px = px0 + j * blockDim.x;
+      if (px >= npix) break;
+      const uint32_t us[3] = {f2ord(v4[j].x), f2ord(v4[j].y), f2ord(v4[j].z)};
+#pragma unroll
+      for (int an = 0; an < 3; ++an) {
+        const uint32_t u = us[an];
+        if (u > T || (take_all_eq && u == T)) {
+          const unsigned pos = atomicAdd(&s_cnt, 1u);
+          if (pos < 1024) keys[pos] = ((unsigned long long)u << 32) | (0xFFFFFFFFu - (uint32_t)(px * 3 + an));
+        }
       }
     }
   }
