@@ -40,14 +40,18 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int
 
 template <typename T>
 __global__ void preprocess_kernel(PreprocessArgs a) {
-  const long long total = (long long)a.B * a.Hp * a.Wx;
+  // one thread per full-resolution pixel slot of the space-to-depth layout: item = ((b, Y, Xc), sub = dy*2+dx)
+  const int Hq = a.Hp / 2;
+  const long long total = (long long)a.B * Hq * a.Wx * 4;
   const T* src = reinterpret_cast<const T*>(a.src);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int xc = (int)(i % a.Wx);
-    const int y = (int)((i / a.Wx) % a.Hp);
-    const int b = (int)(i / ((long long)a.Wx * a.Hp));
-    const int x = xc - 3;
+    const int sub = (int)(i & 3);
+    const int xc = (int)((i >> 2) % a.Wx);
+    const int yq = (int)(((i >> 2) / a.Wx) % Hq);
+    const int b = (int)((i >> 2) / ((long long)a.Wx * Hq));
+    const int x = (xc - 2) * 2 + (sub & 1);
+    const int y = yq * 2 + (sub >> 1);
     float v[3] = {0.f, 0.f, 0.f};
     if (x >= 0 && x < a.Wr && y < a.Hr) {
       int y0, y1, x0, x1;
@@ -77,7 +81,8 @@ __global__ void preprocess_kernel(PreprocessArgs a) {
 }
 
 int launch_preprocess(const PreprocessArgs& a, cudaStream_t s) {
-  const long long total = (long long)a.B * a.Hp * a.Wx;
+  if (a.Hp % 2) { set_error("preprocess: padded height must be even"); return -1; }
+  const long long total = (long long)a.B * (a.Hp / 2) * a.Wx * 4;
   const int g = grid_for(total, 256);
   if (a.src_u8) preprocess_kernel<unsigned char><<<g, 256, 0, s>>>(a);
   else preprocess_kernel<float><<<g, 256, 0, s>>>(a);

@@ -201,11 +201,11 @@ int build_plan(dpb200_session* s) {
   s->Hr = (int)floor((double)s->H0 * s->k);   // F.interpolate: floor(in * scale_factor)
   s->Wr = (int)floor((double)s->W0 * s->k);
   s->Hp = round_up(s->Hr, 32); s->Wp = round_up(s->Wr, 32);
-  s->Wx = s->Wp + 16;
+  s->Wx = s->Wp / 2 + 4;     // space-to-depth row: 2 zero pixels left, 2 right
   const int Hp = s->Hp, Wp = s->Wp;
 
   // ---- a1/a2 preprocess
-  T4 x0 = b.act(B, Hp, s->Wx, 4);
+  T4 x0 = b.act(B, Hp / 2, s->Wx, 16);    // [B, Hp/2, Wp/2+4, (dy, dx, c4)]
   b.tap("stem_in", x0);
   {
     PreprocessArgs& p = s->pre;
@@ -220,14 +220,15 @@ int build_plan(dpb200_session* s) {
       p.src = ss->io->images;
       p.flip_rgb = (ss->m->cfg.input_rgb && ss->io->bgr) ? 1 : 0;   // defaults.py:82-83
       return launch_preprocess(p, st);
-    }, "preprocess", (double)B * s->H0 * s->W0 * 3 * (s->src_u8 ? 1 : 4) + (double)B * Hp * s->Wx * 8);
+    }, "preprocess", (double)B * s->H0 * s->W0 * 3 * (s->src_u8 ? 1 : 4) + (double)B * (Hp / 2) * s->Wx * 32);
   }
-  // ---- a3 stem: 7x7/2 conv as 7 row taps over a 16-pixel (64-element) sliding window
+  // ---- a3 stem: on the space-to-depth input the 7x7/2 conv is a 4x4/1 conv over 16 channels: 4 row taps, each a
+  // window of 4 pixels x 16 channels = 64 contiguous elements (one K chunk) that slides by one pixel (32 B) per output
   T4 stem = b.act(B, Hp / 2, Wp / 2, 64);
   {
-    T4 xv = x0; xv.W = Wp / 2; xv.C = 64;   // virtual [B, Hp, Wp/2, 64] view with overlapping windows
-    Builder::ConvOpt o; o.kh = 7; o.kw = 1; o.sy = 2; o.sx = 1; o.pad_y = 3; o.pad_x = 0; o.relu = 1;
-    o.x_sw = 8; o.x_sh = (long long)s->Wx * 4; o.x_sn = (long long)Hp * s->Wx * 4;
+    T4 xv = x0; xv.H = Hp / 2; xv.W = Wp / 2; xv.C = 64;   // virtual [B, Hp/2, Wp/2, 64] view with overlapping windows
+    Builder::ConvOpt o; o.kh = 4; o.kw = 1; o.sy = 1; o.sx = 1; o.pad_y = 2; o.pad_x = 0; o.relu = 1;
+    o.x_sw = 16; o.x_sh = (long long)s->Wx * 16; o.x_sn = (long long)(Hp / 2) * s->Wx * 16;
     o.H_out = Hp / 2; o.W_out = Wp / 2;
     b.conv("backbone.bottom_up.stem.conv1", xv, stem, o);
   }

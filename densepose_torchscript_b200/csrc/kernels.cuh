@@ -10,8 +10,9 @@ namespace dpb {
 typedef __nv_bfloat16 bf16;
 
 // ---- preprocess (defaults.py:76-89 + rcnn.py:156-181) ------------------------------------------
-// src: [B, H0, W0, 3] fp32 or u8 (HWC). dst: stem layout [B, Hp, Wx, 4] bf16 where image column x sits
-// at x + 3, columns outside [3, 3 + Wr) and rows >= Hr are zero, channel 3 is zero.
+// src: [B, H0, W0, 3] fp32 or u8 (HWC). dst: space-to-depth stem layout [B, Hp/2, Wx, 16] bf16: the padded image
+// pixel (y, x, c) sits at [y/2][x/2 + 2][((y&1)*2 + (x&1))*4 + c]; Wx = Wp/2 + 4 (two zero pixels on either side);
+// everything outside the resized Hr x Wr image and channel 3 of every sub-pixel is zero.
 struct PreprocessArgs {
   const void* src; int src_u8; int B, H0, W0;
   int Hr, Wr;            // resized extents floor(H0*k), floor(W0*k)

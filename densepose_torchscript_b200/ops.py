@@ -90,12 +90,13 @@ def conv2d(x: torch.Tensor, packed: torch.Tensor, bias: Optional[torch.Tensor], 
 
 def preprocess(images: torch.Tensor, k: float, mean: Sequence[float], std: Sequence[float],
                flip_rgb: bool = False) -> Tuple[torch.Tensor, Tuple[int, int, int, int]]:
-    """images [B,H0,W0,3] fp32/u8 cuda -> stem layout [B,Hp,Wp+16,4] bf16. Returns (dst, (Hr,Wr,Hp,Wp))."""
+    """images [B,H0,W0,3] fp32/u8 cuda -> space-to-depth stem layout [B,Hp/2,Wp/2+4,16] bf16 (see `stem_to_image`).
+    Returns (dst, (Hr,Wr,Hp,Wp))."""
     _lib.require_device()
     b, h0, w0, _ = images.shape
     hr, wr = int(math.floor(h0 * k)), int(math.floor(w0 * k))
     hp, wp = round_up(hr, 32), round_up(wr, 32)
-    dst = torch.empty(b, hp, wp + 16, 4, dtype=torch.bfloat16, device=images.device)
+    dst = torch.empty(b, hp // 2, wp // 2 + 4, 16, dtype=torch.bfloat16, device=images.device)
     a = _lib.PreprocessArgs()
     a.src = images.data_ptr(); a.src_u8 = int(images.dtype == torch.uint8)
     a.b, a.h0, a.w0, a.hr, a.wr = b, h0, w0, hr, wr
@@ -103,9 +104,15 @@ def preprocess(images: torch.Tensor, k: float, mean: Sequence[float], std: Seque
     a.flip_rgb = int(flip_rgb)
     for i in range(3):
         a.mean[i] = mean[i]; a.std[i] = std[i]
-    a.dst = dst.data_ptr(); a.hp, a.wx = hp, wp + 16
+    a.dst = dst.data_ptr(); a.hp, a.wx = hp, wp // 2 + 4
     check(lib.dpb200_preprocess(C.byref(a), _stream()), "dpb200_preprocess")
     return dst, (hr, wr, hp, wp)
+
+
+def stem_to_image(dst: torch.Tensor) -> torch.Tensor:
+    """Inverse of the stem layout: [B,Hp/2,Wq,16] -> [B,Hp,2*Wq,4] (padded-image pixel (y,x) at column x + 4)."""
+    b, hq, wq, _ = dst.shape
+    return dst.view(b, hq, wq, 2, 2, 4).permute(0, 1, 3, 2, 4, 5).reshape(b, 2 * hq, 2 * wq, 4)
 
 
 def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:

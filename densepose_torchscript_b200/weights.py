@@ -7,7 +7,7 @@ body_conv_fcnN|stacked_convs.N), with or without the predictor's "model." prefix
 Transforms (all exact re-layouts except the bf16 rounding of the final weights):
   * FrozenBatchNorm2d folded into conv weight + fp32 bias (detectron2/layers/batch_norm.py:45-46, eps 1e-5);
   * OIHW -> K-major [cout_pad][(ky*kw+kx)*cin_pad + ci] bf16 (NHWC implicit-GEMM operand);
-  * stem 7x7/2: per row tap ky a 16-pixel x 4-channel window (kx = pixel 0..6, rest zero);
+  * stem 7x7/2 -> 4x4/1 over the 2x2 space-to-depth image: per row tap a window of 4 pixels x (dy, dx, c4) channels;
   * RPN objectness (3) + anchor deltas (12) fused into one 16-row 1x1 head; cls_score (2) + bbox_pred (4) likewise;
   * FC1 columns permuted from (c,y,x) to the NHWC pooled order (y,x,c) (box_head.py:70-71);
   * the four ConvTranspose2d(k=4,s=2,p=1) predictors concatenated on Cout and split into four 2x2 output-parity
@@ -92,11 +92,21 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], spec: ModelSpec, device) -> Dic
         w, b = _fold(sd, prefix)
         out[prefix] = _pack_conv(w, b if with_bias else None, device)
 
-    # stem: [64,3,7,7] -> [64][ky][16 px][4 ch]
+    # stem: [64,3,7,7] stride 2 pad 3 -> 4x4 stride 1 over the 2x2 space-to-depth input:
+    # [64][ky'][kx'][(dy, dx, c4)] = W[:, c, 2ky'+dy-1, 2kx'+dx-1] (zero outside the 7x7 support)
     w, b = _fold(sd, "backbone.bottom_up.stem.conv1")
-    sw = torch.zeros(64, 7, 16, 4)
-    sw[:, :, :7, :3] = w.permute(0, 2, 3, 1)
-    out["backbone.bottom_up.stem.conv1"] = _pack_khwc(sw.reshape(64, 7, 1, 64), b, device)
+    sw = torch.zeros(64, 4, 4, 2, 2, 4)
+    for kyq in range(4):
+        for dy in range(2):
+            ky = 2 * kyq + dy - 1
+            if not 0 <= ky <= 6:
+                continue
+            for kxq in range(4):
+                for dx in range(2):
+                    kx = 2 * kxq + dx - 1
+                    if 0 <= kx <= 6:
+                        sw[:, kyq, kxq, dy, dx, :3] = w[:, :, ky, kx]
+    out["backbone.bottom_up.stem.conv1"] = _pack_khwc(sw.reshape(64, 4, 1, 64), b, device)
     for si, nb in enumerate(spec.blocks):
         for bi in range(nb):
             p = f"backbone.bottom_up.res{si + 2}.{bi}"

@@ -80,8 +80,9 @@ int dpb200_conv2d(const dpb200_conv2d_args* a, void* stream);
 
 /* DefaultPredictor.forward resize (detectron2/engine/defaults.py:85-89, F.interpolate bilinear,
  * scale_factor=k) fused with GeneralizedRCNN.preprocess_image (meta_arch/rcnn.py:156-181: normalise,
- * zero-pad to /32).  src [B,H0,W0,3] HWC fp32 (or u8); dst = stem layout [B,Hp,Wx,4] bf16, image column x
- * stored at x+3, Wx = Wp+16, everything outside the resized image is 0. */
+ * zero-pad to /32).  src [B,H0,W0,3] HWC fp32 (or u8); dst = space-to-depth stem layout [B,Hp/2,Wx,16] bf16:
+ * padded-image pixel (y,x,c) at [y/2][x/2+2][((y&1)*2+(x&1))*4+c], Wx = Wp/2+4, channel 3 of each sub-pixel and
+ * everything outside the resized image is 0 (on it the 7x7/2 stem conv is a 4x4/1 conv over 16 channels). */
 typedef struct dpb200_preprocess_args {
   const void* src; int32_t src_u8; int32_t b, h0, w0;
   int32_t hr, wr; float inv_scale; int32_t flip_rgb;

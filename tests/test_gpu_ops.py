@@ -177,11 +177,13 @@ def test_preprocess_matches_oracle(ops, h0, w0):
     dst, (hr, wr, hp, wp) = ops.preprocess(img[None].cuda().contiguous(), k, spec.pixel_mean, spec.pixel_std)
     torch.cuda.synchronize()
     assert (hr, wr) == tuple(image.shape[1:]) and (hp, wp) == tuple(ref.shape[2:])
-    got = dst[0, :, 3:3 + wp, :3].permute(2, 0, 1).float().cpu()
+    assert tuple(dst.shape) == (1, hp // 2, wp // 2 + 4, 16)
+    full = ops.stem_to_image(dst)[0]                 # [Hp, Wp + 8, 4], padded-image column x at x + 4
+    got = full[:, 4:4 + wp, :3].permute(2, 0, 1).float().cpu()
     assert frac_equal(got, ref[0]) > 0.995          # identical up to rare 1-ulp bf16 flips (FMA vs mul+add on the host)
     assert float((got - ref[0]).abs().max()) <= 1.0   # one bf16 ulp at |x| in [128, 256)
-    assert bool((dst[0, :, :3] == 0).all()) and bool((dst[0, :, 3 + wp:] == 0).all()) and bool((dst[..., 3] == 0).all())
-    assert bool((dst[0, hr:] == 0).all()) and bool((dst[0, :, 3 + wr:] == 0).all())   # zero padding in normalised space
+    assert bool((full[:, :4] == 0).all()) and bool((full[:, 4 + wp:] == 0).all()) and bool((full[..., 3] == 0).all())
+    assert bool((full[hr:] == 0).all()) and bool((full[:, 4 + wr:] == 0).all())   # zero padding in normalised space
 
 
 def test_maxpool_exact(ops):

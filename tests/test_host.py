@@ -138,10 +138,20 @@ def test_pack_special_layouts_are_exact_relayouts():
             xp = F.pad(x, (1 if px == 0 else 0, 0 if px == 0 else 1, 1 if py == 0 else 0, 0 if py == 0 else 1))
             out[:, :, py::2, px::2] = F.conv2d(xp, w, pk[1][:77])
     assert torch.allclose(out, ref, atol=1e-3)
-    # stem: 7 row taps x 16-pixel window == 7x7 stride-2 conv
+    # stem: 4x4 stride-1 conv over the 2x2 space-to-depth image (channels (dy, dx, c4)) == the 7x7 stride-2 pad-3 conv
     st = packed["backbone.bottom_up.stem.conv1"]
-    w7 = st[0].float().view(64, 7, 16, 4)[:, :, :7, :3].permute(0, 3, 1, 2)
-    assert bool((st[0].float().view(64, 7, 16, 4)[:, :, 7:] == 0).all()) and w7.shape == (64, 3, 7, 7)
+    assert st[0].shape == (64, 4 * 64)
+    w4 = st[0].float().view(64, 4, 4, 16).permute(0, 3, 1, 2)                   # [co, (dy,dx,c4), ky', kx']
+    w7 = sd["backbone.bottom_up.stem.conv1.weight"].float()
+    bn = "backbone.bottom_up.stem.conv1.norm."
+    scale = sd[bn + "weight"].float() * (sd[bn + "running_var"].float() + 1e-5).rsqrt()
+    w7 = (w7 * scale.view(-1, 1, 1, 1)).to(torch.bfloat16).float()
+    xs = torch.randn(1, 3, 20, 28, generator=g)
+    ref7 = F.conv2d(xs, w7, stride=2, padding=3)
+    x4 = torch.zeros(1, 4, 20, 28); x4[:, :3] = xs
+    s2d = x4.view(1, 4, 10, 2, 14, 2).permute(0, 3, 5, 1, 2, 4).reshape(1, 16, 10, 14)    # channel = (dy*2+dx)*4 + c
+    got4 = F.conv2d(F.pad(s2d, (2, 1, 2, 1)), w4)
+    assert got4.shape == ref7.shape and torch.allclose(got4, ref7, atol=1e-4)
 
 
 def test_deeplab_rate56_is_its_centre_tap():

@@ -49,8 +49,9 @@ def main():
           sess.hr, sess.wr, sess.hp, sess.wp)
     sess.run(imgs)
     torch.cuda.synchronize()
-    x0 = sess.tap("stem_in")[0]   # [Hp, Wx, 4]
-    print("stem_in", rel(x0[:, 3:3 + sess.wp, :3].permute(2, 0, 1), taps["images"][0]))
+    from densepose_torchscript_b200.ops import stem_to_image
+    x0 = stem_to_image(sess.tap("stem_in"))[0]   # [Hp, Wp + 8, 4]
+    print("stem_in", rel(x0[:, 4:4 + sess.wp, :3].permute(2, 0, 1), taps["images"][0]))
     for k in ("res2", "res3", "res4", "res5"):
         print(k, rel(nchw(sess.tap(k))[:1], taps["res"][k]))
     for k in ("p2", "p3", "p4", "p5"):
