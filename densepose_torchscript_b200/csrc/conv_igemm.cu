@@ -3,16 +3,20 @@
 // Replaces every F.conv2d / nn.Linear / ConvTranspose2d-phase on the reference hot path
 // (detectron2/layers/wrappers.py:104-112 Conv2d.forward, box_head.py:95-98, chart.py:76-90).
 //
-// GEMM view: M = output pixels (a TMA box of tw x th x tn pixels, <= 128 rows), N = Cout tile
-// (block_n <= 256), K = taps x Cin in 64-channel slabs. Per K-slab the producer issues one 4-D TMA
-// box load of the shifted input window (zero fill outside the image implements the padding) and
-// one 2-D load of the packed weights, both 128B-swizzled; one thread issues four
-// tcgen05.mma (K=16 each) into a TMEM accumulator; four epilogue warps drain TMEM with tcgen05.ld
-// and fuse bias / residual / nearest-x2 top-down add / ReLU / dtype conversion.
+// GEMM view: M = output pixels (128 consecutive (n, oy, ox) pixels per tile through im2col-mode TMA, or a
+// tw x th x tn pixel box through tiled TMA), N = Cout tile (block_n <= 256), K = taps x Cin in 64-channel chunks.
+// Per chunk the producer issues one TMA load of the shifted input window (zero fill outside the image implements
+// the padding) and one 2-D load of the packed weights, both 128B-swizzled; one elected thread issues four
+// tcgen05.mma (K = 16 each) into a double-buffered TMEM accumulator; eight epilogue warps drain TMEM with tcgen05.ld
+// and fuse bias / residual / nearest-x2 top-down add / ReLU / dtype conversion, leaving through swizzled shared
+// memory slabs + TMA stores (bf16 matrix outputs) or direct stores (fp32 / strided / channel-planar outputs).
 //
-// Warp roles (256 threads, persistent, 1 CTA per SM):
-//   warp 0 lane 0 : TMA producer          warp 1 lane 0 : MMA issuer
-//   warp 2        : TMEM alloc / dealloc  warps 4..7    : epilogue (TMEM lane quarter = warp % 4)
+// Warp roles (384 threads, persistent, 1 CTA per SM):
+//   warp 0 : TMA producer              warp 1 : MMA issuer (CTA pairs: the leader CTA only)
+//   warp 2 : TMEM alloc / dealloc, residual prefetch (TMA -> slab)
+//   warp 3 : TMA store issuer          warps 4..11 : epilogue (TMEM lane quarter = warp % 4, column half = (warp-4)/4)
+// Variants selected per layer by conv_plan_build: staged / direct epilogue, CTA pairs (cta_group::2), deconv phases
+// as N blocks (phase_taps). Every launch is a programmatic dependent launch.
 #include "conv_igemm.cuh"
 #include "ptx.cuh"
 #include "device_utils.cuh"
