@@ -126,6 +126,24 @@ def test_batch_images_are_independent_and_deterministic(s1x):
             assert torch.equal(r[k], s[k]), k
 
 
+def test_graph_replay_equals_plain_launches(s1x):
+    """The CUDA-graph replay (programmatic-dependent-launch edges between the convs captured into the graph) and plain
+    stream launches of the same plan give bit-identical outputs, run after run."""
+    from densepose_torchscript_b200.config import BUILTIN
+    from densepose_torchscript_b200.engine import Engine
+    eng, sd = s1x
+    assert eng.use_graph
+    plain = Engine(BUILTIN["densepose_rcnn_R_50_FPN_s1x"], sd, use_graph=False)
+    imgs = torch.stack([W.synthetic_image(240, 600, seed=3), W.synthetic_image(240, 600, seed=9)])
+    ref = [{k: v.clone() for k, v in r.items()} for r in plain.forward_batch(imgs)]
+    for _ in range(3):                      # first call captures, the next ones replay
+        got = eng.forward_batch(imgs)
+        torch.cuda.synchronize()
+        for r, s in zip(got, ref):
+            for k in s:
+                assert torch.equal(r[k], s[k]), k
+
+
 def test_full_size_properties(s1x):
     """BASELINE-size input (800x1333): shapes, ordering, clipping and the zero-detection path."""
     eng, _ = s1x
