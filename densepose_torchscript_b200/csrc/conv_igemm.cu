@@ -475,11 +475,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t aph = 0;
     for (int tile = t_begin; tile < total_tiles; tile += t_step) {
       const int n_blk = tile % p.n_blocks;
-      const int mt = tile / p.n_blocks;
+      int mt = tile / p.n_blocks;
+      if (kPair) {
+        if (mt * 256 >= m_valid) continue;
+        mt = 2 * mt + (int)rank;
+      }
       int ox, oy, on;
       if (p.im2col) {
         const int m0 = mt * 128;
-        if (m0 >= m_valid) continue;
+        if (!kPair && m0 >= m_valid) continue;
         const int m = m0 + row;
         on = m / hw_out;
         const int rem = m - on * hw_out;
@@ -564,7 +568,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(as));
+      if (kPair) {                                  // one arrive per warp on the LEADER's barrier
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0));
+      } else {
+        mbar_arrive(tempty_bar(as));
+      }
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
   }
@@ -765,10 +774,10 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
   // CTA pairs (cta_group::2): staged im2col convs whose N tile splits into two halves of a multiple of 16 rows.
   // Chosen automatically for the long-K, 256-wide tiles (the 3x3 256->256 / 512->512 convs), where halving the
   // weight traffic from L2 pays; d.pair forces it on (2) or off (1).
-  const bool pair_ok = staged && d.im2col && block_n % 32 == 0 && block_n >= 64 && (num_sms & ~1) >= 2;
-  if (d.pair == 2 && !pair_ok) { set_error("conv: pair mode needs a staged im2col conv with block_n %% 32 == 0"); return -1; }
+  const bool pair_ok = d.im2col && block_n % 16 == 0 && block_n >= 32 && (num_sms & ~1) >= 2;
+  if (d.pair == 2 && !pair_ok) { set_error("conv: pair mode needs an im2col conv with block_n %% 16 == 0"); return -1; }
   // (measured on the path's shapes: short-K tiles lose to the pair's extra barrier traffic; K >= 18 chunks gains 6-10 %)
-  const bool pair = d.pair == 2 || (d.pair == 0 && pair_ok && block_n == 256 && k_iters >= 18 && m_total >= 4096);
+  const bool pair = d.pair == 2 || (d.pair == 0 && pair_ok && staged && block_n == 256 && k_iters >= 18 && m_total >= 4096);
   plan->pair = pair ? 1 : 0;
   const int b_rows = pair ? block_n / 2 : block_n;
   const int b_bytes = (b_rows * 128 + 1023) & ~1023;
@@ -866,6 +875,9 @@ int conv_kernels_init() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              227 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024);
   if (e != cudaSuccess) { set_error("conv: smem attr: %s", cudaGetErrorString(e)); return -3; }
   return 0;
 }
@@ -897,8 +909,10 @@ int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = (unsigned)na;
   cudaError_t le;
-  if (plan.pair)
+  if (plan.pair && plan.staged)
     le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, true>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.p);
+  else if (plan.pair)
+    le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, true>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.p);
   else if (plan.staged)
     le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, false>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.p);
   else

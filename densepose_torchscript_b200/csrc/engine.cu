@@ -112,6 +112,7 @@ struct Builder {
     int H_out = 0, W_out = 0;
     bool no_bias = false;
     int phase_taps = 0;
+    int pair = 0;
   };
 
   // y must be allocated by the caller (so views / slices are possible)
@@ -146,6 +147,7 @@ struct Builder {
                    : (void*)(reinterpret_cast<bf16*>(y.p) + o.out_off);
     d.n_valid = o.n_valid;
     d.phase_taps = o.phase_taps;
+    d.pair = o.pair;
     if (d.cout_pad > y.C && !o.out_sx) { fail = -12; set_error("conv %s: output has %d channels, weights %d", wname.c_str(), y.C, d.cout_pad); return; }
     const double fl = 2.0 * x.N * d.H_out * d.W_out * (double)w->cout_pad * d.kh * d.kw * w->cin_pad;
     s->flops += fl;

@@ -69,7 +69,8 @@ typedef struct dpb200_conv2d_args {
                                channels [(2*py+px)*c, +c) of y (h_out = h, w_out = w).                    */
   int32_t pair;             /* CTA pairs: clusters of two CTAs run one tcgen05.mma.cta_group::2 on a 256-row tile,
                                each CTA staging half of the weight tile. 0 automatic (long-K 256-wide tiles), 1 off,
-                               2 on (needs the slab epilogue, tiled == 0 and an N tile that is a multiple of 32) */
+                               2 on (needs tiled == 0 and an N tile that is a multiple of 16; works with both
+                               epilogues; measured neutral for the N=80 deconv phases, so not chosen there) */
 } dpb200_conv2d_args;
 
 int dpb200_conv2d(const dpb200_conv2d_args* a, void* stream);

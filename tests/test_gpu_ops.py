@@ -120,7 +120,7 @@ def test_conv_cta_pairs_match_single_cta_bitwise(ops, case):
         assert bool((flat[first_free:] == -5.0).all())
 
 
-@pytest.mark.parametrize("tiled", [False, True])
+@pytest.mark.parametrize("tiled", [False, True, "pair"])
 def test_deconv_four_phases_in_one_launch(ops, tiled):
     """ConvTranspose2d(k=4,s=2,p=1) (chart.py:45-59) as one GEMM launch whose N blocks are the output-parity phases."""
     from densepose_torchscript_b200.weights import _pack_khwc
@@ -141,7 +141,8 @@ def test_deconv_four_phases_in_one_launch(ops, tiled):
     cp = ph[0][3]
     nv = torch.tensor([4], dtype=torch.int32, device="cuda")
     out = torch.full((R, 4 * cp, P, P), -3.0, device="cuda")
-    ops.conv2d(nhwc_bf16_cuda(x), packed, bias, 2, 2, pad=1, planar=True, out=out, phase_taps=True, tiled=tiled, n_valid=nv)
+    ops.conv2d(nhwc_bf16_cuda(x), packed, bias, 2, 2, pad=1, planar=True, out=out, phase_taps=True, tiled=tiled is True,
+               pair=2 if tiled == "pair" else 1, n_valid=nv)       # "pair": CTA pairs with the direct (fp32, planar) epilogue
     torch.cuda.synchronize()
     low = out.view(R, 2, 2, cp, P, P)[:, :, :, :Cout].cpu()                  # [r, py, px, c, y, x]
     got = low.permute(0, 3, 4, 1, 5, 2).reshape(R, Cout, 2 * P, 2 * P)          # (2y+py, 2x+px)
