@@ -241,3 +241,33 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_header_is_plain_c_and_matches_the_ctypes_structs(tmp_path):
+    """include/dpb200.h compiles as C99 with gcc (no CUDA / C++ types cross the boundary) and every argument struct
+    has the size (and last-field offset) of its ctypes mirror in _lib.py — an ABI drift between the header, the
+    library and the binding would otherwise only show up as garbage on the GPU."""
+    import ctypes as C
+    from densepose_torchscript_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = [("dpb200_conv2d_args", _lib.Conv2dArgs), ("dpb200_preprocess_args", _lib.PreprocessArgs),
+             ("dpb200_rpn_args", _lib.RpnArgs), ("dpb200_roi_align_args", _lib.RoiAlignArgs),
+             ("dpb200_box_predict_args", _lib.BoxPredictArgs), ("dpb200_resample_args", _lib.ResampleArgs),
+             ("dpb200_forward_io", _lib.ForwardIO), ("dpb200_model_config", _lib.ModelConfig),
+             ("dpb200_weight", _lib.Weight)]
+    src = tmp_path / "abi.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dpb200.h"', "int main(void) {"]
+    for cname, ct in pairs:
+        last = ct._fields_[-1][0]
+        lines.append(f'  printf("{cname} %zu %zu\\n", sizeof({cname}), offsetof({cname}, {last}));')
+    lines += ["  return 0;", "}"]
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.split("\n")
+    got = {l.split()[0]: (int(l.split()[1]), int(l.split()[2])) for l in out if l.strip()}
+    for cname, ct in pairs:
+        last = ct._fields_[-1][0]
+        assert got[cname] == (C.sizeof(ct), getattr(ct, last).offset), (cname, got[cname], C.sizeof(ct))
