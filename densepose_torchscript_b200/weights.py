@@ -55,9 +55,14 @@ def canonicalize(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
 
 def _fold(sd, prefix) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     w = sd[prefix + ".weight"].detach().float()
-    if prefix + ".norm.running_var" in sd:
-        scale = sd[prefix + ".norm.weight"].float() * (sd[prefix + ".norm.running_var"].float() + BN_EPS).rsqrt()
-        bias = sd[prefix + ".norm.bias"].float() - sd[prefix + ".norm.running_mean"].float() * scale
+    if prefix + ".norm.running_var" in sd or prefix + ".norm.weight" in sd:
+        # checkpoints without running statistics (Caffe2 AffineChannel blobs) load as mean 0 / var 1
+        # (FrozenBatchNorm2d._load_from_state_dict, detectron2/layers/batch_norm.py:75-82)
+        gamma = sd[prefix + ".norm.weight"].float()
+        var = sd[prefix + ".norm.running_var"].float() if prefix + ".norm.running_var" in sd else torch.ones_like(gamma)
+        mean = sd[prefix + ".norm.running_mean"].float() if prefix + ".norm.running_mean" in sd else torch.zeros_like(gamma)
+        scale = gamma * (var + BN_EPS).rsqrt()
+        bias = sd[prefix + ".norm.bias"].float() - mean * scale
         return w * scale.view(-1, 1, 1, 1), bias
     b = sd.get(prefix + ".bias")
     return w, (b.detach().float() if b is not None else None)

@@ -10,7 +10,6 @@ uses the seeded synthetic weights (no network here to fetch the model zoo).
 """
 import argparse
 import os
-import pickle
 
 import torch
 
@@ -19,19 +18,14 @@ from densepose_torchscript_b200.config import BUILTIN, spec_from_yaml
 from densepose_torchscript_b200.predictor import DensePoseB200Predictor
 
 
-def load_weights(path: str):
-    """detectron2/checkpoint/detection_checkpoint.py:49-90, minus the network handlers and the Caffe2 renames."""
-    if path.endswith(".pkl"):
-        with open(path, "rb") as f:
-            data = pickle.load(f, encoding="latin1")
-        if "model" in data and "__author__" in data:
-            return {k: torch.as_tensor(v) for k, v in data["model"].items()}
-        raise ValueError("Caffe2-format .pkl checkpoints need the detectron2 name conversion (not implemented yet); "
-                         "convert to a detectron2-format .pkl or a state_dict first")
-    data = torch.load(path, map_location="cpu", weights_only=False)
-    if isinstance(data, dict) and "model" in data and isinstance(data["model"], dict):
-        data = data["model"]
-    return data
+def load_weights(path: str, spec=None):
+    """detectron2/checkpoint/detection_checkpoint.py:49-122 without fvcore / iopath: torch files, detectron2 model-zoo
+    pickles and Caffe2 / Detectron1 pickles (blob names converted and attached by suffix, checkpoint.py)."""
+    from densepose_torchscript_b200.checkpoint import load_checkpoint
+    shapes = None
+    if spec is not None and path.endswith(".pkl"):
+        shapes = {k: tuple(v.shape) for k, v in synth.make_state_dict(spec, 0).items()}
+    return load_checkpoint(path, shapes)
 
 
 def main():
@@ -50,7 +44,7 @@ def main():
         spec = replace(BUILTIN[args.cfg], score_thresh=args.min_score)
         if args.nms_thresh is not None:
             spec = replace(spec, nms_test=args.nms_thresh)
-    sd = load_weights(args.weights) if args.weights else synth.make_state_dict(spec, 0)
+    sd = load_weights(args.weights, spec) if args.weights else synth.make_state_dict(spec, 0)
     predictor = DensePoseB200Predictor(spec, sd).eval()
     predictor = torch.jit.script(predictor)
     if args.fp16:

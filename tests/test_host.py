@@ -6,6 +6,7 @@ import re
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -271,3 +272,69 @@ def test_header_is_plain_c_and_matches_the_ctypes_structs(tmp_path):
     for cname, ct in pairs:
         last = ct._fields_[-1][0]
         assert got[cname] == (C.sizeof(ct), getattr(ct, last).offset), (cname, got[cname], C.sizeof(ct))
+
+
+def test_caffe2_blob_names_convert_like_the_reference():
+    """checkpoint.rename_caffe2_key == the reference's convert_c2_detectron_names on every blob of a DensePose R50-FPN
+    (golden mapping generated from the reference by tests/golden/make_c2_names.py; re-derived live when the reference
+    is present)."""
+    import json
+    from densepose_torchscript_b200.checkpoint import rename_caffe2_key
+    here = os.path.dirname(os.path.abspath(__file__))
+    golden = json.load(open(os.path.join(here, "golden", "c2_names.json")))["map"]
+    assert len(golden) > 200
+    for blob, name in golden.items():
+        assert rename_caffe2_key(blob) == name, blob
+    if have_reference():
+        for p in (REFERENCE, os.path.join(ROOT, "oracle", "shims")):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        from detectron2.checkpoint.c2_model_loading import convert_c2_detectron_names
+        _, origin = convert_c2_detectron_names({b: torch.zeros(8, 2) for b in golden})
+        assert {v: k for k, v in origin.items()} == golden
+
+
+def test_caffe2_checkpoint_loads_into_the_reference_key_space(tmp_path):
+    """A Detectron1-style {"blobs": ...} pickle (blob names, background row first in cls_score / bbox_pred, momentum
+    blobs, AffineChannel scale/bias without running statistics) loads to exactly the tensors a detectron2-named
+    state_dict holds, and packs to the same engine weights."""
+    import json
+    import pickle
+    from densepose_torchscript_b200 import synth
+    from densepose_torchscript_b200.checkpoint import load_checkpoint
+    from densepose_torchscript_b200.config import BUILTIN
+    from densepose_torchscript_b200.weights import pack_state_dict
+    spec = BUILTIN["densepose_rcnn_R_50_FPN_s1x_legacy"]
+    sd = synth.make_state_dict(spec, 0)
+    for k in list(sd):                                   # Caffe2 models carry no running statistics
+        if k.endswith("running_mean"):
+            sd[k] = torch.zeros_like(sd[k])
+        if k.endswith("running_var"):
+            sd[k] = torch.ones_like(sd[k])
+    here = os.path.dirname(os.path.abspath(__file__))
+    golden = json.load(open(os.path.join(here, "golden", "c2_names.json")))["map"]
+    blobs = {}
+    for blob, short in golden.items():
+        full = [k for k in sd if k == short or k.endswith("." + short)]
+        assert len(full) == 1, (blob, short, full)
+        v = sd[full[0]]
+        if short.startswith("cls_score."):               # detectron2 keeps the background class last, Caffe2 first
+            v = torch.cat([v[-1:], v[:-1]])
+        if short.startswith("bbox_pred."):               # Caffe2 also regresses a (meaningless) background box
+            v = torch.cat([torch.full_like(v[:4], 7.0), v])
+        blobs[blob] = v.numpy()
+        blobs[blob + "_momentum"] = np.zeros(1, dtype=np.float32)
+    path = tmp_path / "DensePose_ResNet50_FPN_s1x-e2e.pkl"
+    with open(path, "wb") as f:
+        pickle.dump({"blobs": blobs, "cfg": "ignored"}, f)
+    shapes = {k: tuple(v.shape) for k, v in sd.items()}
+    got = load_checkpoint(str(path), shapes)
+    stats = [k for k in sd if k.endswith("running_mean") or k.endswith("running_var")]
+    assert set(got) == set(sd) - set(stats)
+    for k in got:
+        assert torch.equal(got[k], sd[k]), k
+    a, b = pack_state_dict(got, spec, "cpu"), pack_state_dict(sd, spec, "cpu")
+    assert set(a) == set(b)
+    for k in a:
+        assert torch.equal(a[k][0], b[k][0]), k
+        assert (a[k][1] is None and b[k][1] is None) or torch.equal(a[k][1], b[k][1]), k
