@@ -55,7 +55,8 @@ def canonicalize(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
 
 def _fold(sd, prefix) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     w = sd[prefix + ".weight"].detach().float()
-    if prefix + ".norm.running_var" in sd or prefix + ".norm.weight" in sd:
+    frozen_bn = prefix.startswith("backbone.bottom_up.")      # the only FrozenBatchNorm2d layers (DeepLab's `.norm` is GroupNorm)
+    if prefix + ".norm.running_var" in sd or (frozen_bn and prefix + ".norm.weight" in sd):
         # checkpoints without running statistics (Caffe2 AffineChannel blobs) load as mean 0 / var 1
         # (FrozenBatchNorm2d._load_from_state_dict, detectron2/layers/batch_norm.py:75-82)
         gamma = sd[prefix + ".norm.weight"].float()

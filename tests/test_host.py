@@ -155,6 +155,22 @@ def test_pack_special_layouts_are_exact_relayouts():
     assert got4.shape == ref7.shape and torch.allclose(got4, ref7, atol=1e-4)
 
 
+def test_deeplab_groupnorm_is_not_folded_into_the_conv():
+    """DeepLab's `body_conv_fcnN.norm` is a GroupNorm (deeplab.py:45): its affine parameters stay a separate GN op, the
+    packed conv is the raw bf16 weight without bias (only the backbone's FrozenBatchNorm2d layers are folded)."""
+    from densepose_torchscript_b200 import synth
+    from densepose_torchscript_b200.config import BUILTIN
+    from densepose_torchscript_b200.weights import pack_state_dict
+    spec = BUILTIN["densepose_rcnn_R_101_FPN_DL_s1x"]
+    sd = synth.make_state_dict(spec, 0)
+    packed = pack_state_dict(sd, spec, "cpu")
+    k = "roi_heads.densepose_head.body_conv_fcn1"
+    assert packed[k][1] is None
+    w = sd[k + ".weight"].permute(0, 2, 3, 1).reshape(512, -1).to(torch.bfloat16)
+    assert torch.equal(packed[k][0][:512, :w.shape[1]], w)
+    assert torch.equal(packed[k + ".norm"][0], sd[k + ".norm.weight"].float())
+
+
 def test_deeplab_rate56_is_its_centre_tap():
     x = torch.randn(2, 8, 28, 28)
     w = torch.randn(4, 8, 3, 3)
