@@ -354,3 +354,19 @@ def test_caffe2_checkpoint_loads_into_the_reference_key_space(tmp_path):
     for k in a:
         assert torch.equal(a[k][0], b[k][0]), k
         assert (a[k][1] is None and b[k][1] is None) or torch.equal(a[k][1], b[k][1]), k
+
+
+def test_bench_reference_arm_under_torchrun_only_rank0_works():
+    """The driver launches the reference arm like the GPU arm (torchrun, N ranks): rank 0 alone measures and prints
+    the one JSON line, the other ranks exit 0 without work."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+           "--warmup", "0", "--height", "96", "--width", "128"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
