@@ -19,7 +19,9 @@ import torch  # noqa: E402
 from oracle import densepose_oracle as O  # noqa: E402
 from oracle import weights as W  # noqa: E402
 
-CONFIGS = ["densepose_rcnn_R_50_FPN_s1x_legacy", "densepose_rcnn_R_50_FPN_s1x", "densepose_rcnn_R_101_FPN_DL_s1x"]
+# all six published configs (README.md:69-206 of the reference); `python make_golden.py <name> ...` regenerates a subset
+CONFIGS = ["densepose_rcnn_R_50_FPN_s1x_legacy", "densepose_rcnn_R_50_FPN_s1x", "densepose_rcnn_R_101_FPN_DL_s1x",
+           "densepose_rcnn_R_50_FPN_DL_s1x", "densepose_rcnn_R_101_FPN_s1x", "densepose_rcnn_R_101_FPN_s1x_legacy"]
 IMAGE = dict(height=240, width=600, seed=3)
 DP_KEYS = ["pred_densepose_coarse_segm", "pred_densepose_fine_segm", "pred_densepose_u", "pred_densepose_v"]
 
@@ -52,7 +54,7 @@ def summarize(out):
 
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
-    for name in CONFIGS:
+    for name in (sys.argv[1:] or CONFIGS):
         spec = O.SPECS[name]
         sd = W.make_state_dict(spec, 0)
         pred = build_reference(name)

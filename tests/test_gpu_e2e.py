@@ -85,7 +85,8 @@ def test_stages_and_outputs_vs_bf16_oracle(s1x):
 
 
 @pytest.mark.parametrize("name", ["densepose_rcnn_R_50_FPN_s1x_legacy", "densepose_rcnn_R_50_FPN_s1x",
-                                  "densepose_rcnn_R_101_FPN_DL_s1x"])
+                                  "densepose_rcnn_R_101_FPN_DL_s1x", "densepose_rcnn_R_50_FPN_DL_s1x",
+                                  "densepose_rcnn_R_101_FPN_s1x", "densepose_rcnn_R_101_FPN_s1x_legacy"])
 def test_engine_vs_reference_golden(name):
     """Engine (bf16) against outputs of the REAL fp32 reference (tests/golden). Tolerances for bf16 vs fp32:
     >= 70% of reference detections matched within 2 px; score difference of the matched ones: 90th percentile < 3e-2
