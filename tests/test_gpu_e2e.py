@@ -273,3 +273,28 @@ def test_no_detections_gives_correctly_shaped_empty_outputs(name):
     torch.cuda.synchronize()
     assert all(len(r["scores"]) > 0 for r in some)
     assert all(bool(torch.isfinite(r["pred_densepose_u"]).all()) for r in some)
+
+
+def test_channel_order_quirk(s1x):
+    """defaults.py:82-83 (SURVEY quirk 5): only an INPUT.FORMAT == "RGB" model flips the channels of a bgr=True input;
+    with the default BGR config the `bgr` flag changes nothing."""
+    from dataclasses import replace
+
+    from densepose_torchscript_b200.config import BUILTIN
+    from densepose_torchscript_b200.engine import Engine
+    _, sd = s1x
+    base = replace(BUILTIN["densepose_rcnn_R_50_FPN_s1x"], min_size=256, max_size=448)
+    img = W.synthetic_image(128, 192, seed=12)[None]
+    clone = lambda rs: [{k: v.clone() for k, v in r.items()} for r in rs]      # noqa: E731
+    bgr_model = Engine(base, sd)
+    a = clone(bgr_model.forward_batch(img, bgr=True))
+    b = clone(bgr_model.forward_batch(img, bgr=False))
+    for k in a[0]:
+        assert torch.equal(a[0][k], b[0][k]), k
+    rgb_model = Engine(replace(base, input_format="RGB"), sd)
+    c = clone(rgb_model.forward_batch(img, bgr=True))                          # flipped inside
+    d = clone(rgb_model.forward_batch(img.flip(-1).contiguous(), bgr=False))  # flipped by the caller
+    for k in c[0]:
+        assert torch.equal(c[0][k], d[0][k]), k
+    e = clone(rgb_model.forward_batch(img, bgr=False))                         # RGB model, RGB input: no flip
+    assert len(e[0]["scores"]) != len(c[0]["scores"]) or not torch.equal(e[0]["pred_boxes"], c[0]["pred_boxes"])
