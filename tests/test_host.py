@@ -370,3 +370,21 @@ def test_bench_reference_arm_under_torchrun_only_rank0_works():
     assert len(lines) == 1, lines
     line = json.loads(lines[0])
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+
+
+def test_built_library_is_sm100a_tcgen05_code():
+    """The shipped .so holds sm_100a SASS whose conv kernel uses the 5th-generation tensor-core path: tcgen05.mma
+    (UTCHMMA, incl. the 2-CTA form), TMEM loads (LDTM), TMA tensor loads / stores (UTMALDG incl. im2col mode, UTMASTG),
+    cluster-multicast commits (UTCBAR...MULTICAST) — and no legacy mma.sync (HMMA) anywhere."""
+    import shutil
+    from densepose_torchscript_b200 import _lib
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    r = subprocess.run([exe, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    sass = r.stdout
+    assert "sm_100a" in sass
+    for needle in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG.4D.IM2COL", "UTMALDG.2D.2CTA", "UTMASTG.2D", "MULTICAST"):
+        assert needle in sass, needle
+    assert "HMMA" not in sass.replace("UTCHMMA", "")
