@@ -72,7 +72,8 @@ def algorithmic_gflop(spec, hp: int, wp: int, rpn_props: int = 1000):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """Samples SM clock, power and throttle reasons through NVML every 100 ms while the timed region runs."""
+    """Samples SM clock, power and throttle reasons through NVML every 10 ms while the timed region runs (the region
+    is ~0.25 s: about twenty samples)."""
 
     def __init__(self, index: int):
         self.index, self.samples, self._stop, self._thread, self.err = index, [], False, None, None
@@ -106,7 +107,7 @@ class ClockSampler:
             except Exception as e:  # noqa: BLE001
                 self.err = repr(e)
                 return
-            time.sleep(0.1)
+            time.sleep(0.01)
 
     def stop(self):
         self._stop = True
