@@ -500,7 +500,10 @@ def run_ours(a):
         }
         # measured DRAM traffic of the conv launches of one step (ncu capture committed under profiles/)
         traffic, traffic_src = ncu_conv_traffic_gb()
+        n_conv = line["roofline"]["launches_per_step"]
         line["roofline"].update({"traffic": traffic, "traffic_unit": "GB of DRAM read+write per step over the kernel's launches",
+                                 "traffic_per_launch_gb": (traffic / n_conv) if (traffic and n_conv) else None,
+                                 "algorithmic_gb_per_launch": conv_gb / n_conv if n_conv else None,
                                  "traffic_source": traffic_src, "algorithmic_gb_per_step": conv_gb})
         # the memory-bound stage kernels against the measured HBM copy bandwidth
         agg = {}
