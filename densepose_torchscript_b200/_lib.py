@@ -48,6 +48,7 @@ class PreprocessArgs(C.Structure):
         ("src", vp), ("src_u8", i32), ("b", i32), ("h0", i32), ("w0", i32),
         ("hr", i32), ("wr", i32), ("inv_scale", f32), ("flip_rgb", i32),
         ("mean", f32 * 3), ("std", f32 * 3), ("dst", vp), ("hp", i32), ("wx", i32),
+        ("tables", vp), ("variant", i32), ("dst_lo", vp),
     ]
 
 
@@ -117,6 +118,7 @@ _proto("dpb200_abi_version", C.c_int, [])
 _proto("dpb200_device_ok", C.c_int, [])
 _proto("dpb200_conv2d", C.c_int, [C.POINTER(Conv2dArgs), vp])
 _proto("dpb200_preprocess", C.c_int, [C.POINTER(PreprocessArgs), vp])
+_proto("dpb200_u8_resize_tables", C.c_int, [vp, i32, i32, i32, i32, C.c_double, vp])
 _proto("dpb200_maxpool3x3s2", C.c_int, [vp, vp, i32, i32, i32, i32, vp])
 _proto("dpb200_upsample2x", C.c_int, [vp, vp, i32, i32, i32, i32, vp])
 _proto("dpb200_decoder_merge", C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp])
@@ -145,6 +147,7 @@ _proto("dpb200_session_tap", C.c_int, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(
 
 EXPORTS = [
     "dpb200_last_error", "dpb200_abi_version", "dpb200_device_ok", "dpb200_conv2d", "dpb200_preprocess",
+    "dpb200_u8_resize_tables",
     "dpb200_maxpool3x3s2", "dpb200_upsample2x", "dpb200_decoder_merge", "dpb200_rpn_proposals",
     "dpb200_nms_sorted", "dpb200_roi_align", "dpb200_box_predict", "dpb200_groupnorm_relu", "dpb200_avgpool",
     "dpb200_predictor_upsample", "dpb200_dp_resample", "dpb200_model_create", "dpb200_model_destroy",

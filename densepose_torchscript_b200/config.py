@@ -31,6 +31,9 @@ class ModelSpec:
     pixel_mean: Tuple[float, float, float] = (103.530, 116.280, 123.675)
     pixel_std: Tuple[float, float, float] = (1.0, 1.0, 1.0)
     input_format: str = "BGR"       # INPUT.FORMAT
+    uv_confidence: str = ""         # ROI_DENSEPOSE_HEAD.UV_CONFIDENCE: "" (off) | "iid_iso" (WC1: sigma_2 head) |
+                                    # "indep_aniso" (WC2: sigma_2, kappa_u, kappa_v heads)  (chart_with_confidence.py:50-79)
+    segm_confidence: bool = False   # ROI_DENSEPOSE_HEAD.SEGM_CONFIDENCE.ENABLED (WC*M: fine / coarse segm confidence heads)
 
     @property
     def blocks(self) -> Tuple[int, int, int, int]:
@@ -76,18 +79,55 @@ def _load_yaml_with_base(path: str) -> dict:
     return out
 
 
+def _require(cond: bool, what: str):
+    if not cond:
+        raise ValueError("unsupported config: " + what)
+
+
 def spec_from_yaml(path: str, min_score: float = 0.3, nms_thresh: float = None) -> ModelSpec:
-    """export.py:21-33 semantics: yaml (+_BASE_) over the code defaults, then --min_score / --nms_thresh."""
+    """export.py:21-33 semantics: yaml (+_BASE_) over the code defaults, then --min_score / --nms_thresh.
+    Every key that changes the numerics of the hot path is read and either honoured or rejected: a yaml this engine
+    does not implement (other backbone / pooler / predictor / head) raises instead of exporting a model that computes
+    something else."""
+    if not os.path.isfile(path):
+        raise FileNotFoundError(f"config file {path!r} does not exist (builtin names: {', '.join(sorted(BUILTIN))})")
     y = _load_yaml_with_base(path)
     model = y.get("MODEL", {})
     dp = model.get("ROI_DENSEPOSE_HEAD", {})
     name = os.path.splitext(os.path.basename(path))[0]
     head_name = dp.get("NAME", "DensePoseV1ConvXHead")
     heads = {"DensePoseV1ConvXHead": "v1convx", "DensePoseDeepLabHead": "deeplab"}
-    if head_name not in heads:
-        raise ValueError(f"unsupported ROI_DENSEPOSE_HEAD.NAME {head_name}")
-    if model.get("ROI_HEADS", {}).get("NAME", "DensePoseROIHeads") != "DensePoseROIHeads":
-        raise ValueError("only DensePoseROIHeads models are supported")
+    _require(head_name in heads, f"MODEL.ROI_DENSEPOSE_HEAD.NAME {head_name}")
+    _require(model.get("ROI_HEADS", {}).get("NAME", "DensePoseROIHeads") == "DensePoseROIHeads", "only DensePoseROIHeads models")
+    _require(model.get("META_ARCHITECTURE", "GeneralizedRCNN") == "GeneralizedRCNN", "MODEL.META_ARCHITECTURE")
+    _require(model.get("BACKBONE", {}).get("NAME", "build_resnet_fpn_backbone") == "build_resnet_fpn_backbone",
+             f"MODEL.BACKBONE.NAME {model.get('BACKBONE', {}).get('NAME')}")
+    # detectron2/config.py defaults: ROIAlignV2 / sampling 0; the DensePose base yaml sets ROIAlign / 2 for both heads,
+    # which is what the kernels implement (aligned=False, two samples per bin axis)
+    box_head = model.get("ROI_BOX_HEAD", {})
+    _require(box_head.get("POOLER_TYPE", "ROIAlignV2") == "ROIAlign", f"ROI_BOX_HEAD.POOLER_TYPE {box_head.get('POOLER_TYPE', 'ROIAlignV2')}")
+    _require(dp.get("POOLER_TYPE", "ROIAlignV2") == "ROIAlign", f"ROI_DENSEPOSE_HEAD.POOLER_TYPE {dp.get('POOLER_TYPE', 'ROIAlignV2')}")
+    _require(int(box_head.get("POOLER_SAMPLING_RATIO", 0)) == 2, "ROI_BOX_HEAD.POOLER_SAMPLING_RATIO != 2")
+    _require(int(dp.get("POOLER_SAMPLING_RATIO", 2)) == 2, "ROI_DENSEPOSE_HEAD.POOLER_SAMPLING_RATIO != 2")    # densepose/config.py:178
+    _require(int(box_head.get("POOLER_RESOLUTION", 14)) == 7, "ROI_BOX_HEAD.POOLER_RESOLUTION != 7")
+    _require(box_head.get("NAME", "") == "FastRCNNConvFCHead" and int(box_head.get("NUM_FC", 0)) == 2 and
+             int(box_head.get("NUM_CONV", 0)) == 0, "ROI_BOX_HEAD must be FastRCNNConvFCHead with 2 FCs")
+    pred = dp.get("PREDICTOR_NAME", "DensePoseChartPredictor")
+    _require(pred in ("DensePoseChartPredictor", "DensePoseChartWithConfidencePredictor"), f"PREDICTOR_NAME {pred}")
+    _require(int(model.get("ROI_HEADS", {}).get("NUM_CLASSES", 80)) == 1, "ROI_HEADS.NUM_CLASSES != 1")
+    _require(not model.get("MASK_ON", False) and not model.get("KEYPOINT_ON", False), "MASK_ON / KEYPOINT_ON")
+    _require(bool(model.get("DENSEPOSE_ON", False)), "MODEL.DENSEPOSE_ON is false")
+    _require(int(dp.get("NUM_STACKED_CONVS", 8)) == 8 and int(dp.get("CONV_HEAD_DIM", 512)) == 512 and
+             int(dp.get("CONV_HEAD_KERNEL", 3)) == 3, "ROI_DENSEPOSE_HEAD stacked convs must be 8 x 3x3 x 512")
+    _require(int(dp.get("NUM_PATCHES", 24)) == 24, "ROI_DENSEPOSE_HEAD.NUM_PATCHES != 24")
+    _require(int(dp.get("DECONV_KERNEL", 4)) == 4 and int(dp.get("UP_SCALE", 2)) == 2, "DECONV_KERNEL != 4 or UP_SCALE != 2")
+    _require(dp.get("DECODER_NORM", "") == "" and int(dp.get("DECODER_CONV_DIMS", 256)) == 256 and
+             int(dp.get("DECODER_NUM_CLASSES", 256)) == 256 and int(dp.get("DECODER_COMMON_STRIDE", 4)) == 4, "decoder shape")
+    _require(dp.get("DEEPLAB", {}).get("NORM", "GN") == "GN" and int(dp.get("DEEPLAB", {}).get("NONLOCAL_ON", 0)) == 0,
+             "DEEPLAB.NORM != GN or NONLOCAL_ON")
+    mean = tuple(float(v) for v in model.get("PIXEL_MEAN", (103.530, 116.280, 123.675)))
+    std = tuple(float(v) for v in model.get("PIXEL_STD", (1.0, 1.0, 1.0)))
+    _require(len(mean) == 3 and len(std) == 3, "PIXEL_MEAN / PIXEL_STD must have 3 entries")
     spec = ModelSpec(
         name=name,
         depth=int(model.get("RESNETS", {}).get("DEPTH", 50)),
@@ -104,9 +144,15 @@ def spec_from_yaml(path: str, min_score: float = 0.3, nms_thresh: float = None) 
         max_size=int(y.get("INPUT", {}).get("MAX_SIZE_TEST", 1333)),
         input_format=str(y.get("INPUT", {}).get("FORMAT", "BGR")),
         dets_per_image=int(y.get("TEST", {}).get("DETECTIONS_PER_IMAGE", 100)),
+        pixel_mean=mean, pixel_std=std,
+        uv_confidence=(str(dp.get("UV_CONFIDENCE", {}).get("TYPE", "iid_iso"))
+                       if dp.get("UV_CONFIDENCE", {}).get("ENABLED", False) else ""),
+        segm_confidence=bool(dp.get("SEGM_CONFIDENCE", {}).get("ENABLED", False)),
     )
     if nms_thresh is not None:
         spec = replace(spec, nms_test=float(nms_thresh))
-    if spec.depth not in (50, 101):
-        raise ValueError(f"unsupported ResNet depth {spec.depth}")
+    _require(spec.depth in (50, 101), f"ResNet depth {spec.depth}")
+    _require(spec.input_format in ("BGR", "RGB"), f"INPUT.FORMAT {spec.input_format}")
+    _require(spec.pooler_res in (14, 28), f"ROI_DENSEPOSE_HEAD.POOLER_RESOLUTION {spec.pooler_res}")
+    _require(spec.uv_confidence in ("", "iid_iso", "indep_aniso"), f"UV_CONFIDENCE.TYPE {spec.uv_confidence}")
     return spec

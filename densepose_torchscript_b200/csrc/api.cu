@@ -65,7 +65,14 @@ int dpb200_preprocess(const dpb200_preprocess_args* a, void* stream) {
   p.inv_scale = a->inv_scale; p.flip_rgb = a->flip_rgb;
   for (int i = 0; i < 3; ++i) { p.mean[i] = a->mean[i]; p.std[i] = a->std[i]; }
   p.dst = reinterpret_cast<bf16*>(a->dst); p.Hp = a->hp; p.Wx = a->wx;
+  p.tables = reinterpret_cast<const int2*>(a->tables); p.variant = a->variant;
+  p.dst_lo = reinterpret_cast<bf16*>(a->dst_lo);
   return launch_preprocess(p, S(stream));
+}
+
+int dpb200_u8_resize_tables(void* tables, int32_t h0, int32_t hr, int32_t w0, int32_t wr, double scale, void* stream) {
+  if (!tables) { set_error("u8_resize_tables: null table"); return -1; }
+  return launch_u8_resize_tables(reinterpret_cast<int2*>(tables), h0, hr, w0, wr, scale, S(stream));
 }
 
 int dpb200_maxpool3x3s2(const void* x, void* y, int32_t b, int32_t h, int32_t w, int32_t c, void* stream) {

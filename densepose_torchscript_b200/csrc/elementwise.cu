@@ -26,10 +26,16 @@ static inline int grid_for(long long work, int threads, int cap = 148 * 16) {
   } while (0)
 
 // ------------------------------------------------------------------------------------ preprocess
-// ATen upsample_bilinear2d (align_corners=False, scale_factor given): src = s*(dst+0.5)-0.5, s = 1/k.
+// Float images: ATen upsample_bilinear2d (align_corners=False, scale_factor given): src = s*(dst+0.5)-0.5, s = 1/k.
+// The installed ATen CPU build contracts that expression into one FMA and evaluates the taps as
+//   top = fma(lx0, p00, lx1*p01), bot = fma(lx0, p10, lx1*p11), out = fma(ly0, top, ly1*bot)     (variant 0)
+// in its separable generic kernel (what a multi-threaded reference runs for the HWC->CHW permuted image); with ONE
+// intra-op thread ATen picks its channels-last kernel for C == 3, whose scalar loop is
+//   s = fma(w00, p00, w01*p01); s = fma(w10, p10, s); s = fma(w11, p11, s),  wij = lyi*lxj            (variant 1)
+// (probed on torch 2.11 and restated in oracle/aten_interp.py; both reproduced bit for bit here).
 __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int& i0, int& i1,
                                           float& l0, float& l1) {
-  float real = __fsub_rn(__fmul_rn(scale, (float)dst + 0.5f), 0.5f);
+  float real = fmaf(scale, (float)dst + 0.5f, -0.5f);
   if (real < 0.f) real = 0.f;
   i0 = (int)real;
   if (i0 > in_size - 1) i0 = in_size - 1;
@@ -38,12 +44,73 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int
   l0 = __fsub_rn(1.f, l1);
 }
 
+// uint8 images stay uint8 through the reference's resize (run.py:33-36 feeds torch.from_numpy(cv2 image);
+// defaults.py:89). ATen resizes uint8 with the Pillow-style fixed-point scheme: per axis, double-precision triangle
+// weights around center = s*(i+0.5) are normalised and quantised to int16 with the largest precision p (<= 22) that
+// keeps the largest weight below 2^15; the horizontal pass rounds to uint8 ((sum + 2^(p-1)) >> p), then the vertical
+// pass does the same on the rounded rows. One CTA per axis builds the table: entry i = (first tap index, w0 | w1 << 16),
+// tab[0] = (precision of the y axis, precision of the x axis), y entries from tab[1], x entries from tab[1 + Hr].
+__global__ void __launch_bounds__(256)
+u8_resize_tables_kernel(int2* __restrict__ tab, int in_h, int out_h, int in_w, int out_w, double scale) {
+  const int axis = blockIdx.x;
+  const int in_size = axis ? in_w : in_h, out_size = axis ? out_w : out_h;
+  int2* t = tab + 1 + (axis ? out_h : 0);
+  __shared__ double s_max[256];
+  __shared__ int s_prec;
+  auto weights = [&](int i, long long& xmin, double& w0, double& w1) {
+    const double center = __dmul_rn(scale, (double)i + 0.5);
+    long long lo = (long long)__dadd_rn(__dsub_rn(center, 1.0), 0.5);
+    if (lo < 0) lo = 0;
+    long long hi = (long long)__dadd_rn(__dadd_rn(center, 1.0), 0.5);
+    if (hi > in_size) hi = in_size;
+    long long n = hi - lo;
+    n = n < 0 ? 0 : (n > 2 ? 2 : n);
+    double w[2] = {0.0, 0.0}, total = 0.0;
+    for (int j = 0; j < (int)n; ++j) {
+      const double x = fabs(__dadd_rn(__dsub_rn((double)(j + lo), center), 0.5));
+      w[j] = x < 1.0 ? __dsub_rn(1.0, x) : 0.0;
+      total = __dadd_rn(total, w[j]);
+    }
+    if (total != 0.0) { w[0] = __ddiv_rn(w[0], total); w[1] = __ddiv_rn(w[1], total); }
+    xmin = lo; w0 = w[0]; w1 = n > 1 ? w[1] : 0.0;
+  };
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < out_size; i += blockDim.x) {
+    long long xmin; double w0, w1;
+    weights(i, xmin, w0, w1);
+    mx = fmax(mx, fmax(w0, w1));
+  }
+  s_max[threadIdx.x] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int i = 0; i < (int)blockDim.x; ++i) m = fmax(m, s_max[i]);
+    int p = 0;
+    for (; p < 22; ++p) {
+      const int next_value = (int)__dadd_rn(0.5, __dmul_rn(m, (double)(1 << (p + 1))));
+      if (next_value >= (1 << 15)) break;
+    }
+    s_prec = p;
+    if (axis) tab[0].y = p; else tab[0].x = p;
+  }
+  __syncthreads();
+  const double unit = (double)(1 << s_prec);
+  for (int i = threadIdx.x; i < out_size; i += blockDim.x) {
+    long long xmin; double w0, w1;
+    weights(i, xmin, w0, w1);
+    const int q0 = (int)__dadd_rn(0.5, __dmul_rn(w0, unit)), q1 = (int)__dadd_rn(0.5, __dmul_rn(w1, unit));   // weights are >= 0
+    t[i] = make_int2((int)xmin, (q0 & 0xffff) | (q1 << 16));
+  }
+}
+
 template <typename T>
 __global__ void preprocess_kernel(PreprocessArgs a) {
   // one thread per full-resolution pixel slot of the space-to-depth layout: item = ((b, Y, Xc), sub = dy*2+dx)
   const int Hq = a.Hp / 2;
   const long long total = (long long)a.B * Hq * a.Wx * 4;
   const T* src = reinterpret_cast<const T*>(a.src);
+  int prec_y = 0, prec_x = 0;
+  if (sizeof(T) == 1) { const int2 hdr = a.tables[0]; prec_y = hdr.x; prec_x = hdr.y; }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int sub = (int)(i & 3);
@@ -54,34 +121,73 @@ __global__ void preprocess_kernel(PreprocessArgs a) {
     const int y = yq * 2 + (sub >> 1);
     float v[3] = {0.f, 0.f, 0.f};
     if (x >= 0 && x < a.Wr && y < a.Hr) {
-      int y0, y1, x0, x1;
-      float ly0, ly1, lx0, lx1;
-      src_index(a.inv_scale, y, a.H0, y0, y1, ly0, ly1);
-      src_index(a.inv_scale, x, a.W0, x0, x1, lx0, lx1);
       const T* base = src + (long long)b * a.H0 * a.W0 * 3;
-      const T* p00 = base + ((long long)y0 * a.W0 + x0) * 3;
-      const T* p01 = base + ((long long)y0 * a.W0 + x1) * 3;
-      const T* p10 = base + ((long long)y1 * a.W0 + x0) * 3;
-      const T* p11 = base + ((long long)y1 * a.W0 + x1) * 3;
+      if (sizeof(T) == 1) {
+        const int2 ty = a.tables[1 + y], tx = a.tables[1 + a.Hr + x];
+        const int y0 = ty.x, y1 = min(y0 + 1, a.H0 - 1), x0 = tx.x, x1 = min(x0 + 1, a.W0 - 1);
+        const int wy0 = ty.y & 0xffff, wy1 = ty.y >> 16, wx0 = tx.y & 0xffff, wx1 = tx.y >> 16;
+        const T* p00 = base + ((long long)y0 * a.W0 + x0) * 3;
+        const T* p01 = base + ((long long)y0 * a.W0 + x1) * 3;
+        const T* p10 = base + ((long long)y1 * a.W0 + x0) * 3;
+        const T* p11 = base + ((long long)y1 * a.W0 + x1) * 3;
+        const int hx = 1 << (prec_x - 1), hy = 1 << (prec_y - 1);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int cs = a.flip_rgb ? 2 - c : c;
-        const float top = __fadd_rn(__fmul_rn(lx0, (float)p00[cs]), __fmul_rn(lx1, (float)p01[cs]));
-        const float bot = __fadd_rn(__fmul_rn(lx0, (float)p10[cs]), __fmul_rn(lx1, (float)p11[cs]));
-        float r = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
-        if (sizeof(T) == 1) r = fminf(fmaxf(rintf(r), 0.f), 255.f);  // uint8 images stay uint8 in the reference
-        v[c] = __fdiv_rn(__fsub_rn(r, a.mean[c]), a.std[c]);
+        for (int c = 0; c < 3; ++c) {
+          const int cs = a.flip_rgb ? 2 - c : c;
+          const int top = min(((int)p00[cs] * wx0 + (int)p01[cs] * wx1 + hx) >> prec_x, 255);
+          const int bot = min(((int)p10[cs] * wx0 + (int)p11[cs] * wx1 + hx) >> prec_x, 255);
+          const int r = min((top * wy0 + bot * wy1 + hy) >> prec_y, 255);
+          v[c] = __fdiv_rn(__fsub_rn((float)r, a.mean[c]), a.std[c]);
+        }
+      } else {
+        int y0, y1, x0, x1;
+        float ly0, ly1, lx0, lx1;
+        src_index(a.inv_scale, y, a.H0, y0, y1, ly0, ly1);
+        src_index(a.inv_scale, x, a.W0, x0, x1, lx0, lx1);
+        const T* p00 = base + ((long long)y0 * a.W0 + x0) * 3;
+        const T* p01 = base + ((long long)y0 * a.W0 + x1) * 3;
+        const T* p10 = base + ((long long)y1 * a.W0 + x0) * 3;
+        const T* p11 = base + ((long long)y1 * a.W0 + x1) * 3;
+        const float w00 = __fmul_rn(ly0, lx0), w01 = __fmul_rn(ly0, lx1), w10 = __fmul_rn(ly1, lx0), w11 = __fmul_rn(ly1, lx1);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int cs = a.flip_rgb ? 2 - c : c;
+          float r;
+          if (a.variant == 0) {
+            const float top = fmaf(lx0, (float)p00[cs], __fmul_rn(lx1, (float)p01[cs]));
+            const float bot = fmaf(lx0, (float)p10[cs], __fmul_rn(lx1, (float)p11[cs]));
+            r = fmaf(ly0, top, __fmul_rn(ly1, bot));
+          } else {
+            r = fmaf(w00, (float)p00[cs], __fmul_rn(w01, (float)p01[cs]));
+            r = fmaf(w10, (float)p10[cs], r);
+            r = fmaf(w11, (float)p11[cs], r);
+          }
+          v[c] = __fdiv_rn(__fsub_rn(r, a.mean[c]), a.std[c]);
+        }
       }
     }
     uint2 o;
     o.x = pack_bf16(v[0], v[1]);
     o.y = pack_bf16(v[2], 0.f);
     reinterpret_cast<uint2*>(a.dst)[i] = o;
+    if (a.dst_lo != nullptr) {      // strict mode: x = hi + lo, lo = bf16(x - hi)
+      uint2 l;
+      l.x = pack_bf16(__fsub_rn(v[0], bf16_lo(o.x)), __fsub_rn(v[1], bf16_hi(o.x)));
+      l.y = pack_bf16(__fsub_rn(v[2], bf16_lo(o.y)), 0.f);
+      reinterpret_cast<uint2*>(a.dst_lo)[i] = l;
+    }
   }
+}
+
+int launch_u8_resize_tables(int2* tab, int H0, int Hr, int W0, int Wr, double scale, cudaStream_t s) {
+  u8_resize_tables_kernel<<<2, 256, 0, s>>>(tab, H0, Hr, W0, Wr, scale);
+  DPB_CHECK_LAUNCH("u8_resize_tables");
+  return 0;
 }
 
 int launch_preprocess(const PreprocessArgs& a, cudaStream_t s) {
   if (a.Hp % 2) { set_error("preprocess: padded height must be even"); return -1; }
+  if (a.src_u8 && a.tables == nullptr) { set_error("preprocess: uint8 input needs the resize tables (dpb200_u8_resize_tables)"); return -1; }
   const long long total = (long long)a.B * (a.Hp / 2) * a.Wx * 4;
   const int g = grid_for(total, 256);
   if (a.src_u8) preprocess_kernel<unsigned char><<<g, 256, 0, s>>>(a);
@@ -469,93 +575,16 @@ int launch_avgpool(const bf16* x, bf16* y, int R, int HW, int C, const int* n_va
 }
 
 // ------------------------------------------------------------------------------------ predictor tail
-// CTA (kb, roi) stages kPairs+1 consecutive low-res rows in shared memory (NHWC, as the deconv GEMM wrote them)
-// and writes the 2*kPairs output rows between them. Work item = (channel c, 8 output columns): lanes run
-// along c (conflict-free smem reads), every thread emits full 32-byte sectors of an NCHW plane.
-// Output row 2k+1 mixes low rows (k, k+1) with weights (.75, .25), row 2k+2 with (.25, .75); k = -1 and
-// k = S-1 collapse onto the edge row (ATen upsample_bilinear2d, align_corners=False, chart.py:62-74).
-static constexpr int kUpPairs = 3;
-
-__global__ void __launch_bounds__(256)
-predictor_upsample_kernel(const float* __restrict__ low, int S, int Cpad, int Kc,
-                          const int* __restrict__ n_valid, float* __restrict__ coarse,
-                          float* __restrict__ fine, float* __restrict__ u, float* __restrict__ v) {
-  const int r = blockIdx.y;
-  if (n_valid != nullptr && r >= *n_valid) return;
-  const int k0 = (int)blockIdx.x * kUpPairs - 1;           // first pair index handled here
-  extern __shared__ __align__(16) float sm[];              // [kUpPairs + 1][S][Cpad]
-  const int row_elems = S * Cpad;
-  for (int j = 0; j <= kUpPairs; ++j) {
-    int ry = k0 + j;
-    ry = ry < 0 ? 0 : (ry > S - 1 ? S - 1 : ry);
-    const float4* src = reinterpret_cast<const float4*>(low + ((long long)r * S + ry) * row_elems);
-    float4* dst = reinterpret_cast<float4*>(sm + j * row_elems);
-    for (int i = threadIdx.x; i < row_elems / 4; i += blockDim.x) dst[i] = __ldg(src + i);
-  }
-  __syncthreads();
-  const int So = 2 * S;
-  const int C = Kc + 75;
-  const int items = C * (S / 4);
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int g = it / C, c = it - g * C;
-    float* dst; int cc, nc;
-    if (c < Kc) { dst = coarse; cc = c; nc = Kc; }
-    else if (c < Kc + 25) { dst = fine; cc = c - Kc; nc = 25; }
-    else if (c < Kc + 50) { dst = u; cc = c - Kc - 25; nc = 25; }
-    else { dst = v; cc = c - Kc - 50; nc = 25; }
-    float* plane = dst + ((long long)r * nc + cc) * So * So + 8 * g;
-    const int xm = 4 * g - 1 < 0 ? 0 : 4 * g - 1;
-    const int xp = 4 * g + 4 > S - 1 ? S - 1 : 4 * g + 4;
-    // horizontal pass per staged row: h[j][t] = (1-lx_t) * v[x0_t] + lx_t * v[x1_t]
-    float a[6], lo[8], hi[8];
-    const float lx0 = (g == 0) ? 0.f : 0.75f;               // output column 0 clamps to the edge
-    auto hrow = [&](int j, float* h) {
-      const float* p = sm + j * row_elems + c;
-      a[0] = p[xm * Cpad];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) a[1 + t] = p[(4 * g + t) * Cpad];
-      a[5] = p[xp * Cpad];
-      h[0] = (1.f - lx0) * a[0] + lx0 * a[1];
-#pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        h[1 + 2 * t] = 0.75f * a[1 + t] + 0.25f * a[2 + t];
-        h[2 + 2 * t] = 0.25f * a[1 + t] + 0.75f * a[2 + t];
-      }
-      h[7] = 0.75f * a[4] + 0.25f * a[5];
-    };
-    hrow(0, lo);
-#pragma unroll
-    for (int j = 0; j < kUpPairs; ++j) {
-      const int k = k0 + j;
-      if (k > S - 1) break;
-      hrow(j + 1, hi);
-      if (k >= 0) {                                         // row 2k+1: (.75, .25)
-        float o[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = 0.75f * lo[t] + 0.25f * hi[t];
-        float4* q = reinterpret_cast<float4*>(plane + (long long)(2 * k + 1) * So);
-        q[0] = make_float4(o[0], o[1], o[2], o[3]);
-        q[1] = make_float4(o[4], o[5], o[6], o[7]);
-      }
-      if (k < S - 1) {                                      // row 2k+2: (.25, .75); k = -1 -> row 0 = edge row
-        float o[8];
-        const float ly = (k < 0) ? 0.f : 0.75f;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = (1.f - ly) * lo[t] + ly * hi[t];
-        float4* q = reinterpret_cast<float4*>(plane + (long long)(2 * k + 2) * So);
-        q[0] = make_float4(o[0], o[1], o[2], o[3]);
-        q[1] = make_float4(o[4], o[5], o[6], o[7]);
-      }
-#pragma unroll
-      for (int t = 0; t < 8; ++t) lo[t] = hi[t];
-    }
-  }
-}
-
-// Same operation on the phase-planar layout the deconv GEMM epilogue writes: low[r][py][px][c][S/2][S/2]
-// holds low-res pixel (2*yy+py, 2*xx+px). No shared memory: lanes run along x, so the loads (4 B, neighbouring
-// lanes adjacent) and the 16-byte stores are both coalesced; each thread walks kUpRows output-row pairs of
-// one 4-column strip and carries the horizontally interpolated row between them.
+// interp2d (chart.py:62-74): F.interpolate(scale_factor=2, bilinear, align_corners=False) of the four deconv outputs,
+// reading the phase-planar layout the deconv GEMM epilogue writes: low[r][py][px][c][S/2][S/2] holds low-res pixel
+// (2*yy+py, 2*xx+px). No shared memory: lanes run along x, so the loads (4 B, neighbouring lanes adjacent) and the
+// 16-byte stores are both coalesced; each thread walks kUpRows output-row pairs of one 4-column strip.
+// The fp32 results reproduce ATen's CPU kernel bit for bit (oracle/aten_interp.py): output 2m+1 = taps (m, m+1) with
+// weights (.75, .25), output 2m = taps (m-1, m) with (.25, .75), edges clamped, and
+//   output h + w > 128 (S = 56):  separable, top = fma(lx0, p00, lx1*p01), out = fma(ly0, top, ly1*bot);
+//   output h + w <= 128 (S = 28, the legacy heads): ATen's channels-last kernel on wij = lyi*lxj — channels below
+//   C - C % 8 of each tensor: s = fma(w11,p11, w10*p10); s = fma(w01,p01,s); s = fma(w00,p00,s); the tail channels:
+//   s = fma(w00,p00, w01*p01); s = fma(w10,p10,s); s = fma(w11,p11,s).
 static constexpr int kUpRows = 10;
 
 // four consecutive output values: fp32 (16-byte store) or fp16 (8-byte store, round to nearest even)
@@ -569,7 +598,23 @@ __device__ __forceinline__ void store4(__half* p, float a, float b, float c, flo
   *reinterpret_cast<uint2*>(p) = o;
 }
 
-template <typename OutT>
+// l0 * a + l1 * b the way ATen's separable kernel rounds it
+__device__ __forceinline__ float lerp_sep(float l0, float a, float l1, float b) { return fmaf(l0, a, __fmul_rn(l1, b)); }
+// the channels-last kernel's four-tap sum (vec: the 8-lane vector expression, else the scalar tail)
+__device__ __forceinline__ float lerp_cl(bool vec, float w00, float p00, float w01, float p01, float w10, float p10,
+                                         float w11, float p11) {
+  float s;
+  if (vec) {
+    s = fmaf(w11, p11, __fmul_rn(w10, p10));
+    s = fmaf(w01, p01, s);
+    return fmaf(w00, p00, s);
+  }
+  s = fmaf(w00, p00, __fmul_rn(w01, p01));
+  s = fmaf(w10, p10, s);
+  return fmaf(w11, p11, s);
+}
+
+template <typename OutT, bool kSmall>
 __global__ void __launch_bounds__(256)
 predictor_upsample_planar_kernel(const float* __restrict__ low, int S, int Cpad, int Kc,
                                  const int* __restrict__ n_valid, OutT* __restrict__ coarse,
@@ -590,88 +635,75 @@ predictor_upsample_planar_kernel(const float* __restrict__ low, int S, int Cpad,
   else if (c < Kc + 25) { dst = fine; cc = c - Kc; nc = 25; }
   else if (c < Kc + 50) { dst = u; cc = c - Kc - 25; nc = 25; }
   else { dst = v; cc = c - Kc - 50; nc = 25; }
+  const bool vec = cc < nc - (nc & 7);
   OutT* plane = dst + ((long long)r * nc + cc) * So * So + 4 * g;
   const long long plane_sz = (long long)Sh * Sh;
   const float* lr = low + ((long long)r * 4 * Cpad + c) * plane_sz;     // + (py*2+px)*Cpad*plane_sz
   // low columns 2g-1, 2g, 2g+1, 2g+2 (clamped): (phase px, column xx) of each
   const int xa = g == 0 ? 0 : g - 1, pa = g == 0 ? 0 : 1;
   const int xd = g == G - 1 ? Sh - 1 : g + 1, pd = g == G - 1 ? 1 : 0;
-  const float lx0 = (g == 0) ? 0.f : 0.75f;    // output column 0 clamps to the edge
-  auto hrow = [&](int y, float* h) {
+  // horizontal weights of the strip's four output columns: (l0, l1) on taps (a0,a1), (a1,a2), (a1,a2), (a2,a3)
+  const float e0 = g == 0 ? 1.f : 0.25f, e1 = g == 0 ? 0.f : 0.75f;       // output column 0 clamps to the edge
+  auto taps = [&](int y, float* t) {
     y = y < 0 ? 0 : (y > S - 1 ? S - 1 : y);
     const float* p0 = lr + (long long)((y & 1) * 2) * Cpad * plane_sz + (long long)(y >> 1) * Sh;
     const float* p1 = p0 + (long long)Cpad * plane_sz;
-    const float a0 = __ldg((pa ? p1 : p0) + xa), a1 = __ldg(p0 + g), a2 = __ldg(p1 + g),
-                a3 = __ldg((pd ? p1 : p0) + xd);
-    h[0] = (1.f - lx0) * a0 + lx0 * a1;
-    h[1] = 0.75f * a1 + 0.25f * a2;
-    h[2] = 0.25f * a1 + 0.75f * a2;
-    h[3] = 0.75f * a2 + 0.25f * a3;
+    t[0] = __ldg((pa ? p1 : p0) + xa); t[1] = __ldg(p0 + g); t[2] = __ldg(p1 + g); t[3] = __ldg((pd ? p1 : p0) + xd);
+  };
+  auto hrow = [&](const float* t, float* h) {
+    h[0] = lerp_sep(e0, t[0], e1, t[1]);
+    h[1] = lerp_sep(0.75f, t[1], 0.25f, t[2]);
+    h[2] = lerp_sep(0.25f, t[1], 0.75f, t[2]);
+    h[3] = lerp_sep(0.75f, t[2], 0.25f, t[3]);
+  };
+  // one output row from the taps of low rows (lo, hi) with vertical weights (ly0, ly1)
+  auto emit = [&](int orow, const float* tl, const float* th, const float* hl, const float* hh, float ly0, float ly1) {
+    float o[4];
+    if (kSmall) {
+      o[0] = lerp_cl(vec, __fmul_rn(ly0, e0), tl[0], __fmul_rn(ly0, e1), tl[1], __fmul_rn(ly1, e0), th[0], __fmul_rn(ly1, e1), th[1]);
+      o[1] = lerp_cl(vec, ly0 * 0.75f, tl[1], ly0 * 0.25f, tl[2], ly1 * 0.75f, th[1], ly1 * 0.25f, th[2]);
+      o[2] = lerp_cl(vec, ly0 * 0.25f, tl[1], ly0 * 0.75f, tl[2], ly1 * 0.25f, th[1], ly1 * 0.75f, th[2]);
+      o[3] = lerp_cl(vec, ly0 * 0.75f, tl[2], ly0 * 0.25f, tl[3], ly1 * 0.75f, th[2], ly1 * 0.25f, th[3]);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) o[t] = lerp_sep(ly0, hl[t], ly1, hh[t]);
+    }
+    store4(plane + (long long)orow * So, o[0], o[1], o[2], o[3]);
   };
   const int k0 = kb * kUpRows - 1;
-  float lo[4], hi[4];
-  hrow(k0, lo);
+  float tl[4], th[4], hl[4], hh[4];
+  taps(k0, tl);
+  hrow(tl, hl);
 #pragma unroll
   for (int j = 0; j < kUpRows; ++j) {
     const int k = k0 + j;
     if (k > S - 1) break;
-    hrow(k + 1, hi);
-    if (k >= 0) {
-      store4(plane + (long long)(2 * k + 1) * So, 0.75f * lo[0] + 0.25f * hi[0], 0.75f * lo[1] + 0.25f * hi[1],
-             0.75f * lo[2] + 0.25f * hi[2], 0.75f * lo[3] + 0.25f * hi[3]);
-    }
-    if (k < S - 1) {
-      const float ly = (k < 0) ? 0.f : 0.75f, hy = 1.f - ly;
-      store4(plane + (long long)(2 * k + 2) * So, hy * lo[0] + ly * hi[0], hy * lo[1] + ly * hi[1],
-             hy * lo[2] + ly * hi[2], hy * lo[3] + ly * hi[3]);
-    }
+    taps(k + 1, th);
+    hrow(th, hh);
+    if (k >= 0) emit(2 * k + 1, tl, th, hl, hh, 0.75f, 0.25f);                    // row 2k+1: taps (k, k+1), weights (.75, .25)
+    if (k < S - 1) emit(2 * k + 2, tl, th, hl, hh, k < 0 ? 1.f : 0.25f, k < 0 ? 0.f : 0.75f);   // row 2k+2; k = -1 -> row 0 = edge row
 #pragma unroll
-    for (int t = 0; t < 4; ++t) lo[t] = hi[t];
+    for (int t = 0; t < 4; ++t) { tl[t] = th[t]; hl[t] = hh[t]; }
   }
 }
 
-static constexpr size_t kUpMaxSmem = 96 * 1024;
-int stage_kernels_init() {
-  cudaError_t e = cudaFuncSetAttribute(predictor_upsample_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpMaxSmem);
-  if (e != cudaSuccess) { set_error("predictor_upsample smem attr: %s", cudaGetErrorString(e)); return -3; }
-  return 0;
-}
+int stage_kernels_init() { return 0; }
 
 int launch_predictor_upsample(const float* low, int R, int S, int Cpad, int Kc, const int* n_valid,
                               void* coarse, void* fine, void* u, void* v, int planar, int out_half,
                               cudaStream_t s) {
-  if (planar) {
-    if (S % 2 || Kc + 75 > Cpad) { set_error("predictor_upsample: bad shape S %d Cpad %d", S, Cpad); return -1; }
-    if (R == 0) return 0;
-    const int KB = (S + 1 + kUpRows - 1) / kUpRows;
-    const int items = KB * (Kc + 75) * (S / 2);
-    dim3 grid((items + 255) / 256, R);
-    if (out_half)
-      predictor_upsample_planar_kernel<__half><<<grid, 256, 0, s>>>(low, S, Cpad, Kc, n_valid, (__half*)coarse,
-                                                                  (__half*)fine, (__half*)u, (__half*)v);
-    else
-      predictor_upsample_planar_kernel<float><<<grid, 256, 0, s>>>(low, S, Cpad, Kc, n_valid, (float*)coarse,
-                                                                 (float*)fine, (float*)u, (float*)v);
-    DPB_CHECK_LAUNCH("predictor_upsample_planar");
-    return 0;
-  }
-  if (out_half) { set_error("predictor_upsample: fp16 output needs the phase-planar layout"); return -1; }
-  if (S % 4 || Cpad % 4 || Kc + 75 > Cpad) { set_error("predictor_upsample: bad shape S %d Cpad %d", S, Cpad); return -1; }
-  const size_t smem = (size_t)(kUpPairs + 1) * S * Cpad * sizeof(float);
-  if (smem > kUpMaxSmem) { set_error("predictor_upsample: S %d Cpad %d needs %zu B of shared memory", S, Cpad, smem); return -1; }
-  static thread_local int init_dev = -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (init_dev != dev) {
-    if (stage_kernels_init()) return -3;
-    init_dev = dev;
-  }
+  if (!planar) { set_error("predictor_upsample: only the phase-planar layout [R,2,2,Cpad,S/2,S/2] is supported"); return -1; }
+  if (S % 2 || Kc + 75 > Cpad) { set_error("predictor_upsample: bad shape S %d Cpad %d", S, Cpad); return -1; }
   if (R == 0) return 0;
-  dim3 grid((S + 1 + kUpPairs - 1) / kUpPairs, R);
-  predictor_upsample_kernel<<<grid, 256, smem, s>>>(low, S, Cpad, Kc, n_valid, (float*)coarse, (float*)fine,
-                                                    (float*)u, (float*)v);
-  DPB_CHECK_LAUNCH("predictor_upsample");
+  const int KB = (S + 1 + kUpRows - 1) / kUpRows;
+  const int items = KB * (Kc + 75) * (S / 2);
+  dim3 grid((items + 255) / 256, R);
+  const bool small = 4 * S <= 128;      // ATen switches kernels on output h + w = 2S + 2S
+#define DPB_UP(T, SM) predictor_upsample_planar_kernel<T, SM><<<grid, 256, 0, s>>>(low, S, Cpad, Kc, n_valid, (T*)coarse, (T*)fine, (T*)u, (T*)v)
+  if (out_half) { if (small) DPB_UP(__half, true); else DPB_UP(__half, false); }
+  else { if (small) DPB_UP(float, true); else DPB_UP(float, false); }
+#undef DPB_UP
+  DPB_CHECK_LAUNCH("predictor_upsample_planar");
   return 0;
 }
 

@@ -31,6 +31,7 @@ struct TensorInfo { void* p; int64_t shape[4]; int dtype; };
 
 struct T4 {           // NHWC activation
   void* p = nullptr; int N = 0, H = 0, W = 0, C = 0; int fp32 = 0;
+  void* p2 = nullptr;   // strict numerics: the low half of the bf16 hi/lo split (same layout as p)
   long long elems() const { return (long long)N * H * W * C; }
 };
 
@@ -216,7 +217,17 @@ int build_plan(dpb200_session* s) {
     p.flip_rgb = 0;
     for (int i = 0; i < 3; ++i) { p.mean[i] = cfg.pixel_mean[i]; p.std[i] = cfg.pixel_std[i]; }
     p.dst = reinterpret_cast<bf16*>(x0.p); p.Hp = Hp; p.Wx = s->Wx;
+    p.dst_lo = reinterpret_cast<bf16*>(x0.p2);
+    p.variant = 0; p.tables = nullptr;
     dpb200_session* ss = s;
+    if (s->src_u8) {
+      // uint8 frames (run.py:33-36): ATen's fixed-point weights, rebuilt on the device every run (two small CTAs)
+      int2* tab = (int2*)b.alloc((size_t)(1 + s->Hr + s->Wr) * sizeof(int2));
+      p.tables = tab;
+      const double scale = 1.0 / s->k;
+      const int H0 = s->H0, W0 = s->W0, Hr = s->Hr, Wr = s->Wr;
+      b.op([=](cudaStream_t st) { return launch_u8_resize_tables(tab, H0, Hr, W0, Wr, scale, st); }, "u8_resize_tables");
+    }
     b.op([ss](cudaStream_t st) {
       PreprocessArgs p = ss->pre;
       p.src = ss->io->images;

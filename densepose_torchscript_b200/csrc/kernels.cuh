@@ -18,10 +18,16 @@ struct PreprocessArgs {
   int Hr, Wr;            // resized extents floor(H0*k), floor(W0*k)
   float inv_scale;       // (float)(1.0 / k)
   int flip_rgb;          // 1: swap channel 0 and 2 (INPUT.FORMAT == RGB and bgr input)
-  float mean[3], inv_std_is_one, std[3];
+  float mean[3], std[3];
   bf16* dst; int Hp, Wx;
+  const int2* tables;    // uint8 input: fixed-point resize tables [1 + Hr + Wr] built by launch_u8_resize_tables
+  int variant;           // float input: 0 = ATen's separable kernel (multi-threaded reference), 1 = its channels-last
+                         // kernel (what a single-threaded reference runs for a 3-channel image)
+  bf16* dst_lo;          // strict mode: low half of the bf16 hi/lo split (else null)
 };
 int launch_preprocess(const PreprocessArgs& a, cudaStream_t s);
+// ATen's uint8 bilinear weights (int16 fixed point, double-precision centres) for both axes: tab[1 + Hr + Wr] int2.
+int launch_u8_resize_tables(int2* tab, int H0, int Hr, int W0, int Wr, double scale, cudaStream_t s);
 
 // ---- 3x3 stride-2 pad-1 max pool, NHWC bf16 (resnet.py:353) -------------------------------------
 int launch_maxpool3x3s2(const bf16* x, bf16* y, int B, int H, int W, int C, cudaStream_t s);

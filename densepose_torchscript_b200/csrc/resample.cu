@@ -6,10 +6,17 @@
 
 namespace dpb {
 
+// ATen's CPU upsample_bilinear2d, reproduced bit for bit (probed on torch 2.11, restated in oracle/aten_interp.py):
+//  * source index: one FMA, real = fma(scale, dst + 0.5, -0.5), scale = float(in) / float(out);
+//  * output h + w > 128: the separable generic kernel,
+//        top = fma(lx0, p00, lx1*p01); bot = fma(lx0, p10, lx1*p11); out = fma(ly0, top, ly1*bot);
+//  * output h + w <= 128: the channels-last kernel (wij = lyi*lxj rounded), 8 channels per vector; channels below
+//    C - C % 8 take the vector expression, the rest the scalar tail — the two associate differently:
+//        vector:  s = fma(w11, p11, w10*p10); s = fma(w01, p01, s); s = fma(w00, p00, s)
+//        tail:    s = fma(w00, p00, w01*p01); s = fma(w10, p10, s); s = fma(w11, p11, s)
 __device__ __forceinline__ void size_index(float scale, int dst, int in_size, int& i0, int& i1, float& l0,
                                            float& l1) {
-  // ATen area_pixel_compute_source_index (align_corners=False) + guard_index_and_lambda
-  float real = __fsub_rn(__fmul_rn(scale, (float)dst + 0.5f), 0.5f);
+  float real = fmaf(scale, (float)dst + 0.5f, -0.5f);
   if (real < 0.f) real = 0.f;
   i0 = (int)real;
   if (i0 > in_size - 1) i0 = in_size - 1;
@@ -39,24 +46,39 @@ __global__ void __launch_bounds__(256) dp_resample_kernel(ResampleArgs a) {
     size_index((float)S / (float)w, ox, S, x0, x1, lx0, lx1);
     const long long o00 = (long long)y0 * S + x0, o01 = (long long)y0 * S + x1;
     const long long o10 = (long long)y1 * S + x0, o11 = (long long)y1 * S + x1;
-    auto sample = [&](const float* pl) -> float {
-      const float top = __fadd_rn(__fmul_rn(lx0, __ldg(pl + o00)), __fmul_rn(lx1, __ldg(pl + o01)));
-      const float bot = __fadd_rn(__fmul_rn(lx0, __ldg(pl + o10)), __fmul_rn(lx1, __ldg(pl + o11)));
-      return __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+    const bool small = h + w <= 128;
+    const float w00 = __fmul_rn(ly0, lx0), w01 = __fmul_rn(ly0, lx1), w10 = __fmul_rn(ly1, lx0), w11 = __fmul_rn(ly1, lx1);
+    // channel c of a tensor with C channels
+    auto sample = [&](const float* pl, int c, int C) -> float {
+      const float p00 = __ldg(pl + o00), p01 = __ldg(pl + o01), p10 = __ldg(pl + o10), p11 = __ldg(pl + o11);
+      if (!small) {
+        const float top = fmaf(lx0, p00, __fmul_rn(lx1, p01));
+        const float bot = fmaf(lx0, p10, __fmul_rn(lx1, p11));
+        return fmaf(ly0, top, __fmul_rn(ly1, bot));
+      }
+      float s;
+      if (c < C - (C & 7)) {
+        s = fmaf(w11, p11, __fmul_rn(w10, p10));
+        s = fmaf(w01, p01, s);
+        return fmaf(w00, p00, s);
+      }
+      s = fmaf(w00, p00, __fmul_rn(w01, p01));
+      s = fmaf(w10, p10, s);
+      return fmaf(w11, p11, s);
     };
     // coarse argmax (first maximum wins, like torch.argmax)
     const float* cbase = a.coarse + (long long)d * a.Kc * plane;
     int carg = 0;
-    float cbest = sample(cbase);
+    float cbest = sample(cbase, 0, a.Kc);
     for (int c = 1; c < a.Kc; ++c) {
-      const float v = sample(cbase + c * plane);
+      const float v = sample(cbase + c * plane, c, a.Kc);
       if (v > cbest) { cbest = v; carg = c; }
     }
     const float* fbase = a.fine + (long long)d * 25 * plane;
     int farg = 0;
-    float fbest = sample(fbase);
+    float fbest = sample(fbase, 0, 25);
     for (int c = 1; c < 25; ++c) {
-      const float v = sample(fbase + c * plane);
+      const float v = sample(fbase + c * plane, c, 25);
       if (v > fbest) { fbest = v; farg = c; }
     }
     const int label = (carg > 0) ? farg : 0;
@@ -64,8 +86,8 @@ __global__ void __launch_bounds__(256) dp_resample_kernel(ResampleArgs a) {
     else reinterpret_cast<long long*>(a.labels)[p] = (long long)label;
     float uu = 0.f, vv = 0.f;
     if (label > 0) {
-      uu = sample(a.u + ((long long)d * 25 + label) * plane);
-      vv = sample(a.v + ((long long)d * 25 + label) * plane);
+      uu = sample(a.u + ((long long)d * 25 + label) * plane, label, 25);
+      vv = sample(a.v + ((long long)d * 25 + label) * plane, label, 25);
     }
     const long long hw = (long long)w * h;
     float* uvb = a.uv + 2 * a.offsets[d];

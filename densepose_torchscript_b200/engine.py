@@ -121,23 +121,25 @@ class Session:
         nb = numel * torch.empty(0, dtype=dtype).element_size()
         return self.workspace[off:off + nb].view(dtype).view(shape[0], shape[1], shape[2], shape[3])
 
-    def results(self) -> List[Dict[str, torch.Tensor]]:
-        """Per-image result dicts in the reference's output format (synchronises)."""
-        spec = self.engine.spec
+    def results(self, copy: bool = True) -> List[Dict[str, torch.Tensor]]:
+        """Per-image result dicts in the reference's output format (synchronises). copy=True (default) returns fresh
+        tensors; copy=False returns VIEWS of this session's persistent output buffers, which the next run() of the
+        session overwrites in place (zero-copy fast path for callers that consume the results first)."""
         counts = self.det_count.cpu().tolist()
         offs = self.det_offsets.cpu().tolist()
+        own = (lambda t: t.clone()) if copy else (lambda t: t)
         out = []
         for b in range(self.batch):
             d, o = counts[b], offs[b]
             out.append({
                 "image_size": torch.tensor([self.h0, self.w0], dtype=torch.int64, device=self.engine.device),
-                "pred_boxes": self.pred_boxes[b, :d],
-                "scores": self.scores[b, :d],
+                "pred_boxes": own(self.pred_boxes[b, :d]),
+                "scores": own(self.scores[b, :d]),
                 "pred_classes": torch.zeros(d, dtype=torch.int64, device=self.engine.device),
-                "pred_densepose_coarse_segm": self.coarse[o:o + d],
-                "pred_densepose_fine_segm": self.fine[o:o + d],
-                "pred_densepose_u": self.u[o:o + d],
-                "pred_densepose_v": self.v[o:o + d],
+                "pred_densepose_coarse_segm": own(self.coarse[o:o + d]),
+                "pred_densepose_fine_segm": own(self.fine[o:o + d]),
+                "pred_densepose_u": own(self.u[o:o + d]),
+                "pred_densepose_v": own(self.v[o:o + d]),
             })
         return out
 
@@ -147,12 +149,13 @@ class Engine:
 
     def __init__(self, spec: ModelSpec, state_dict: Optional[Dict[str, torch.Tensor]] = None,
                  packed: Optional[Dict[str, Packed]] = None, device: Optional[torch.device] = None,
-                 use_graph: bool = True, max_sessions: int = 4):
+                 use_graph: bool = True, max_sessions: int = 4, strict: bool = False):
         """max_sessions: how many plain (slot 0) sessions of distinct shapes stay cached; each owns a workspace
         (0.9 GB at batch 1, 7.1 GB at batch 8 for R50-s1x), so a stream of differently sized images must not
         accumulate them. The least recently used one is dropped; HostPipeline slots are released by close()."""
         _lib.require_device()
         self.spec = spec
+        self.strict = strict
         self.max_sessions = max(1, max_sessions)
         self.use_graph = use_graph
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -206,8 +209,11 @@ class Engine:
         self._sessions[key] = s                                   # (re)insert as most recently used
         return s
 
-    def forward_batch(self, images: torch.Tensor, bgr: bool = True, out_half: bool = False) -> List[Dict[str, torch.Tensor]]:
-        """images [B,H,W,3] (HWC, fp32 or uint8) on any device -> list of reference-format result dicts."""
+    def forward_batch(self, images: torch.Tensor, bgr: bool = True, out_half: bool = False,
+                      copy: bool = True) -> List[Dict[str, torch.Tensor]]:
+        """images [B,H,W,3] (HWC, fp32 or uint8) on any device -> list of reference-format result dicts.
+        copy=False returns views of the session's output buffers (see Session.results): they are overwritten by the
+        next forward_batch of the same (batch, H, W, dtype)."""
         images = images.to(self.device, non_blocking=True).contiguous()
         if images.dtype not in (torch.uint8, torch.float32):
             images = images.float()
@@ -215,7 +221,7 @@ class Engine:
                          out_half=out_half)
         with torch.cuda.device(self.device):
             s.run(images, bgr)
-        return s.results()
+        return s.results(copy=copy)
 
 
 class HostPipeline:
@@ -227,8 +233,16 @@ class HostPipeline:
             done = pipe.submit(frames)    # results of the batch submitted `depth` calls ago (or None)
         tail = pipe.drain()
 
-    Every submit() enqueues H2D copy -> forward -> D2H copy of the reference-format outputs on the slot's
-    stream. Returned host tensors are views of the slot's pinned buffers: valid until that slot is reused.
+    submit() enqueues H2D copy -> forward -> D2H of boxes / scores / counts on the slot's stream. When a slot is
+    collected (the submit() `depth` calls later, or drain()) the DensePose tensors come back COUNT-AWARE: the rows are
+    packed by `det_offsets` on the device, so only the `dp_total` rows that hold detections cross PCIe, not the
+    B x dets_per_image capacity (386 MB per image at 100 detections, 3.9 MB per detection). Those copies run on the
+    collected slot's stream while the other slots' forwards keep the GPU busy.
+
+    Lifetime of returned tensors: they are views of pinned host buffers owned by the pipeline. Two result sets
+    rotate, and a call never writes into the set the previous call handed out: results returned by one submit() stay
+    valid until the NEXT submit() has returned; drain() reuses both sets, so consume (or copy) earlier results before
+    calling it. Copy what must live longer.
 
     extract=True is the run.py flow (run.py:33-57 + visualizer.py:46-56) as a pipeline: only boxes / scores /
     counts come back after the forward; when a slot is collected, the per-box resample + part argmax + U/V gather
@@ -244,6 +258,7 @@ class HostPipeline:
         if extract and out_half:
             raise ValueError("extract=True reads the fp32 DensePose tensors on the device; out_half is for full outputs")
         self.extract_d2h_bytes = 0          # bytes of the last collected extraction (data dependent)
+        self.last_d2h_bytes = 0             # bytes the last collected batch moved device -> host (count-aware)
         self.slots = []
         dt = torch.uint8 if src_u8 else torch.float32
         with torch.cuda.device(engine.device):
@@ -251,15 +266,26 @@ class HostPipeline:
                 sess = engine.session(batch, h0, w0, src_u8, slot=i + 1, out_half=out_half)
                 dev_in = torch.empty(batch, h0, w0, 3, dtype=dt, device=engine.device)
                 host_in = torch.empty(batch, h0, w0, 3, dtype=dt).pin_memory()
-                outs_dev = [sess.pred_boxes, sess.scores, sess.det_count, sess.det_offsets]
-                if not extract:
-                    outs_dev += [sess.coarse, sess.fine, sess.u, sess.v]
-                outs_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs_dev]
-                self.slots.append(dict(sess=sess, dev_in=dev_in, host_in=host_in, outs_dev=outs_dev,
-                                       outs_host=outs_host, done=torch.cuda.Event(), busy=False,
+                small_dev = [sess.pred_boxes, sess.scores, sess.det_count, sess.det_offsets]
+                small_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in small_dev]
+                self.slots.append(dict(sess=sess, dev_in=dev_in, host_in=host_in, small_dev=small_dev,
+                                       small_host=small_host, done=torch.cuda.Event(), busy=False,
                                        ex_dev=None, ex_host=None))
+            # two rotating result sets for the big tensors (full capacity, pinned): the set handed to the caller by one
+            # call is never the one the next call fills
+            s0 = self.slots[0]["sess"]
+            self.big_dev_names = ("coarse", "fine", "u", "v")
+            self.sets = []
+            if not extract:
+                for _ in range(2):
+                    self.sets.append([torch.empty(getattr(s0, n).shape, dtype=getattr(s0, n).dtype).pin_memory()
+                                      for n in self.big_dev_names])
+        self._set = 0
         self.h2d_bytes = self.slots[0]["host_in"].numel() * self.slots[0]["host_in"].element_size()
-        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.slots[0]["outs_host"])
+        self.small_d2h_bytes = sum(t.numel() * t.element_size() for t in self.slots[0]["small_host"])
+        self.row_bytes = 0 if extract else sum(t[0].numel() * t.element_size() for t in self.sets[0])
+        # capacity figure (every row): what a count-unaware copy would move per step
+        self.d2h_bytes = self.small_d2h_bytes + self.row_bytes * batch * engine.spec.dets_per_image
         self._next = 0
 
     def close(self):
@@ -270,16 +296,28 @@ class HostPipeline:
                 if v is sess:
                     del self.engine._sessions[k]
         self.slots = []
+        self.sets = []
 
     def _collect(self, sl) -> Optional[List[Dict[str, torch.Tensor]]]:
         if not sl["busy"]:
             return None
         sl["done"].synchronize()
         sl["busy"] = False
+        # boxes / scores / counts leave the slot's staging buffers (the slot is re-enqueued right after this)
+        boxes, scores, counts, offs = [t.clone() for t in sl["small_host"]]
         if self.extract:
-            return self._collect_extracted(sl)
-        boxes, scores, counts, offs, coarse, fine, u, v = sl["outs_host"]
+            return self._collect_extracted(sl, boxes, scores, counts)
         sess = sl["sess"]
+        n = int(offs[sess.batch])                      # dp_total: rows that hold detections
+        host = self.sets[self._set]
+        self._set ^= 1
+        if n:
+            with torch.cuda.device(self.engine.device), torch.cuda.stream(sess.stream):
+                for hbuf, name in zip(host, self.big_dev_names):
+                    hbuf[:n].copy_(getattr(sess, name)[:n], non_blocking=True)
+            sess.stream.synchronize()
+        self.last_d2h_bytes = self.small_d2h_bytes + n * self.row_bytes
+        coarse, fine, u, v = host
         out = []
         for b in range(sess.batch):
             d, o = int(counts[b]), int(offs[b])
@@ -290,9 +328,8 @@ class HostPipeline:
                         "pred_densepose_u": u[o:o + d], "pred_densepose_v": v[o:o + d]})
         return out
 
-    def _collect_extracted(self, sl) -> List[Dict[str, object]]:
+    def _collect_extracted(self, sl, boxes, scores, counts) -> List[Dict[str, object]]:
         from . import ops
-        boxes, scores, counts, offs = sl["outs_host"]
         sess = sl["sess"]
         dev = self.engine.device
         cnt = [int(c) for c in counts]
@@ -320,6 +357,7 @@ class HostPipeline:
                 ex_host[1][:2 * total].copy_(ex_dev[1][:2 * total], non_blocking=True)
             sess.stream.synchronize()
         self.extract_d2h_bytes = total * (lab_b + 8)
+        self.last_d2h_bytes = self.small_d2h_bytes + self.extract_d2h_bytes
         out, k = [], 0
         for b in range(sess.batch):
             dens = []
@@ -347,17 +385,21 @@ class HostPipeline:
         with torch.cuda.device(self.engine.device), torch.cuda.stream(sess.stream):
             sl["dev_in"].copy_(src, non_blocking=True)
             sess.run(sl["dev_in"], bgr)
-            for hbuf, dbuf in zip(sl["outs_host"], sl["outs_dev"]):
+            for hbuf, dbuf in zip(sl["small_host"], sl["small_dev"]):
                 hbuf.copy_(dbuf, non_blocking=True)
             sl["done"].record(sess.stream)
         sl["busy"] = True
         return prev
 
     def drain(self) -> List[List[Dict[str, torch.Tensor]]]:
+        """Collects every batch still in flight, oldest first. With full outputs the two rotating result sets can hold
+        two batches: draining more than two in-flight batches copies the older ones out of the pinned sets."""
         out = []
         for i in range(self.depth):
             sl = self.slots[(self._next + i) % self.depth]
             r = self._collect(sl)
             if r is not None:
+                if not self.extract and len(out) >= 1 and self.depth > 2:
+                    out[-1] = [{k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in d.items()} for d in out[-1]]
                 out.append(r)
         return out

@@ -1,4 +1,5 @@
-"""Device-side replacement for the reference's per-box result extraction (visualizer.py:10-56).
+"""Device-side replacement for the reference's per-box result extraction (visualizer.py:10-56) and its drawing
+(visualizer.py:59-139).
 
 `DensePoseResultExtractor()(instances)` returns the same structure as the reference — a list with one
 {'labels': int64 [h, w], 'uv': float32 [2, h, w]} per detection, plus boxes_xywh — but the bilinear resize,
@@ -30,12 +31,19 @@ class DensePoseResultExtractor:
 
 
 class End2EndVisualizer:
-    """visualizer.py:132-139: blends the part-label map (I channel) over the image with a JET colormap."""
+    """visualizer.py:96-139 (DensePoseResultsFineSegmentationVisualizer + MatrixVisualizer + End2EndVisualizer): the
+    part-label map (I channel) through `cmap` (VIRIDIS like the reference), blended with `alpha` over each box; with
+    keep_bg=False (what run.py:17 asks for) the whole frame is first blended towards colormap(0) (`fill`,
+    visualizer.py:89-91). Same numpy / cv2 arithmetic as the reference, so the written frames are identical."""
 
-    def __init__(self, alpha: float = 0.7, inplace: bool = True):
+    def __init__(self, alpha: float = 0.7, cmap: Optional[int] = None, keep_bg: bool = True, inplace: bool = True):
+        import cv2
         self.extractor = DensePoseResultExtractor()
         self.alpha = alpha
+        self.cmap = cv2.COLORMAP_VIRIDIS if cmap is None else cmap
+        self.keep_bg = keep_bg
         self.inplace = inplace
+        self.val_scale = 255 / 24                       # visualizer.py:97
 
     def visualize(self, image_bgr: Any, outputs: Dict[str, torch.Tensor]):
         img = image_bgr if self.inplace else image_bgr.copy()
@@ -48,18 +56,23 @@ class End2EndVisualizer:
         import cv2
         import numpy as np
 
-        boxes = boxes_xywh.long().cpu().tolist()
-        for res, (x, y, w, h) in zip(results, boxes):
-            labels = res["labels"].to(torch.uint8).cpu().numpy()
-            h_, w_ = labels.shape
-            x0, y0 = max(x, 0), max(y, 0)
-            x1, y1 = min(x + w_, img.shape[1]), min(y + h_, img.shape[0])
-            if x1 <= x0 or y1 <= y0:
+        if not self.keep_bg:                            # MatrixVisualizer.fill(image_bgr, 0)
+            img[:] = (cv2.applyColorMap(np.array(0, dtype=np.uint8), self.cmap).reshape((1, 1, 3)) * self.alpha +
+                      img * (1.0 - self.alpha))
+        boxes = boxes_xywh.cpu().numpy()
+        for res, box in zip(results, boxes):
+            # iuv_array[0] of visualizer.py:121: the labels as bytes; matrix = segm = the I channel (:106-110)
+            matrix = res["labels"].to(torch.uint8).cpu().numpy()
+            x, y, w, h = [int(v) for v in box]          # MatrixVisualizer.visualize (:73-87)
+            if w <= 0 or h <= 0:
                 continue
-            sub = labels[y0 - y:y1 - y, x0 - x:x1 - x]
-            color = cv2.applyColorMap((sub.astype(np.float32) * (255.0 / 24.0)).astype(np.uint8), cv2.COLORMAP_JET)
-            mask = (sub > 0)[..., None]
-            roi = img[y0:y1, x0:x1]
-            blended = (roi.astype(np.float32) * (1 - self.alpha) + color.astype(np.float32) * self.alpha).astype(np.uint8)
-            img[y0:y1, x0:x1] = np.where(mask, blended, roi)
+            mask = np.zeros(matrix.shape, dtype=np.uint8)
+            mask[matrix > 0] = 1
+            if (w != mask.shape[1]) or (h != mask.shape[0]):
+                mask, matrix = cv2.resize(mask, (w, h)), cv2.resize(matrix, (w, h))
+            mask_bg = np.tile((mask == 0)[:, :, np.newaxis], [1, 1, 3])
+            matrix_scaled_8u = (matrix.astype(np.float32) * self.val_scale).clip(0, 255).astype(np.uint8)
+            matrix_vis = cv2.applyColorMap(matrix_scaled_8u, self.cmap)
+            matrix_vis[mask_bg] = img[y: y + h, x: x + w, :][mask_bg]
+            img[y: y + h, x: x + w, :] = img[y: y + h, x: x + w, :] * (1.0 - self.alpha) + matrix_vis * self.alpha
         return img

@@ -89,9 +89,10 @@ def conv2d(x: torch.Tensor, packed: torch.Tensor, bias: Optional[torch.Tensor], 
 
 
 def preprocess(images: torch.Tensor, k: float, mean: Sequence[float], std: Sequence[float],
-               flip_rgb: bool = False) -> Tuple[torch.Tensor, Tuple[int, int, int, int]]:
+               flip_rgb: bool = False, variant: int = 0) -> Tuple[torch.Tensor, Tuple[int, int, int, int]]:
     """images [B,H0,W0,3] fp32/u8 cuda -> space-to-depth stem layout [B,Hp/2,Wp/2+4,16] bf16 (see `stem_to_image`).
-    Returns (dst, (Hr,Wr,Hp,Wp))."""
+    uint8 images go through ATen's fixed-point uint8 bilinear (tables built on the device first); `variant` picks the
+    float kernel of a multi-threaded (0) or single-threaded (1) reference. Returns (dst, (Hr,Wr,Hp,Wp))."""
     _lib.require_device()
     b, h0, w0, _ = images.shape
     hr, wr = int(math.floor(h0 * k)), int(math.floor(w0 * k))
@@ -102,9 +103,14 @@ def preprocess(images: torch.Tensor, k: float, mean: Sequence[float], std: Seque
     a.b, a.h0, a.w0, a.hr, a.wr = b, h0, w0, hr, wr
     a.inv_scale = float(torch.tensor(1.0 / k, dtype=torch.float64).to(torch.float32))
     a.flip_rgb = int(flip_rgb)
+    a.variant = variant
     for i in range(3):
         a.mean[i] = mean[i]; a.std[i] = std[i]
     a.dst = dst.data_ptr(); a.hp, a.wx = hp, wp // 2 + 4
+    if images.dtype == torch.uint8:
+        tables = torch.empty(1 + hr + wr, 2, dtype=torch.int32, device=images.device)
+        check(lib.dpb200_u8_resize_tables(tables.data_ptr(), h0, hr, w0, wr, 1.0 / k, _stream()), "dpb200_u8_resize_tables")
+        a.tables = tables.data_ptr()
     check(lib.dpb200_preprocess(C.byref(a), _stream()), "dpb200_preprocess")
     return dst, (hr, wr, hp, wp)
 
@@ -241,19 +247,16 @@ def avgpool(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
-def predictor_upsample(low: torch.Tensor, kc: int, planar: bool = False):
-    """low [R,S,S,Cpad] fp32 NHWC (or, planar=True, the phase-planar [R,2,2,Cpad,S/2,S/2] the deconv GEMM
-    writes) -> (coarse [R,kc,2S,2S], fine, u, v) NCHW fp32."""
-    if planar:
-        r, _, _, cpad, sh, _ = low.shape
-        s = 2 * sh
-    else:
-        r, s, _, cpad = low.shape
+def predictor_upsample(low: torch.Tensor, kc: int):
+    """low: the phase-planar fp32 [R,2,2,Cpad,S/2,S/2] the deconv GEMM writes (low-res pixel (2*yy+py, 2*xx+px) at
+    [r,py,px,c,yy,xx]) -> (coarse [R,kc,2S,2S], fine, u, v) NCHW fp32."""
+    r, _, _, cpad, sh, _ = low.shape
+    s = 2 * sh
     dev = low.device
     assert low.is_contiguous() and low.dtype == torch.float32
     outs = [torch.empty(r, c, 2 * s, 2 * s, device=dev) for c in (kc, 25, 25, 25)]
     check(lib.dpb200_predictor_upsample(low.data_ptr(), r, s, cpad, kc, None, *[o.data_ptr() for o in outs],
-                                        int(planar), _stream()), "dpb200_predictor_upsample")
+                                        1, _stream()), "dpb200_predictor_upsample")
     return outs
 
 

@@ -7,6 +7,8 @@ reference's run.py imports torchvision "for its ops", run.py:7).
 
 There is deliberately no CPU implementation: calling the op with CPU weights raises.
 """
+import os
+from collections import OrderedDict
 from typing import Dict, List, Tuple
 
 import torch
@@ -20,7 +22,17 @@ _LIB.define("forward(Tensor image, bool bgr, Tensor blob, int[] table, str[] nam
             "Tensor dtype_probe) -> Tensor[]")
 
 _DT = {0: torch.bfloat16, 1: torch.float32}
-_ENGINES: Dict[Tuple[int, int], Engine] = {}
+# Engines behind exported modules, least recently used first. The key names the weight storage, the device AND the
+# configuration lists, so two modules that share a blob but differ in thresholds get their own engine. The cache is
+# bounded (DPB200_MAX_ENGINES, default 4): an engine pins its weights and up to `max_sessions` workspaces (0.9-7 GB
+# each), so a process that keeps loading / moving modules must not accumulate them; `release_engines()` drops all.
+_ENGINES: "OrderedDict[Tuple, Engine]" = OrderedDict()
+_MAX_ENGINES = max(1, int(os.environ.get("DPB200_MAX_ENGINES", "4")))
+
+
+def release_engines() -> None:
+    """Frees every cached engine (weights stay with their modules; workspaces and sessions are released)."""
+    _ENGINES.clear()
 
 
 def spec_to_lists(spec: ModelSpec) -> Tuple[List[int], List[float]]:
@@ -79,7 +91,7 @@ def unpack_blob(blob: torch.Tensor, table: List[int], names: List[str]):
 
 
 def _engine_for(blob: torch.Tensor, table: List[int], names: List[str], cfg_i: List[int], cfg_f: List[float]) -> Engine:
-    key = (blob.data_ptr(), blob.get_device())
+    key = (blob.data_ptr(), blob.get_device(), tuple(cfg_i), tuple(cfg_f))
     eng = _ENGINES.get(key)
     if eng is None:
         spec = lists_to_spec(cfg_i, cfg_f)
@@ -88,7 +100,11 @@ def _engine_for(blob: torch.Tensor, table: List[int], names: List[str], cfg_i: L
         packed = {k: (v[0].view(v[3], -1) if v[0].dtype == torch.bfloat16 else v[0], v[1], v[2], v[3]) for k, v in packed.items()}
         eng = Engine(spec, packed=packed, device=blob.device)
         eng._blob = blob    # keeps the storage alive for the engine's lifetime
-        _ENGINES[key] = eng
+        while len(_ENGINES) >= _MAX_ENGINES:
+            _ENGINES.popitem(last=False)
+    else:
+        del _ENGINES[key]
+    _ENGINES[key] = eng     # most recently used last
     return eng
 
 
@@ -115,7 +131,7 @@ def _forward_cuda(image, bgr, blob, table, names, cfg_i, cfg_f, dtype_probe):
         image = image.float()
     dt = dtype_probe.dtype if dtype_probe.dtype in (torch.float16, torch.bfloat16) else torch.float32
     # a `.half()` module gets its DensePose tensors as fp16 straight from the kernel (no conversion pass)
-    res = eng.forward_batch(image.unsqueeze(0), bgr, out_half=(dt == torch.float16))[0]
+    res = eng.forward_batch(image.unsqueeze(0), bgr, out_half=(dt == torch.float16), copy=False)[0]   # cloned below
     return [res["image_size"], res["pred_boxes"].clone(), res["scores"].to(dt, copy=True), res["pred_classes"],
             res["pred_densepose_coarse_segm"].to(dt, copy=True), res["pred_densepose_fine_segm"].to(dt, copy=True),
             res["pred_densepose_u"].to(dt, copy=True), res["pred_densepose_v"].to(dt, copy=True)]

@@ -41,6 +41,9 @@ def main():
         spec = spec_from_yaml(args.cfg, min_score=args.min_score, nms_thresh=args.nms_thresh)
     else:
         from dataclasses import replace
+        if args.cfg not in BUILTIN:
+            raise SystemExit(f"{args.cfg!r} is neither a config file nor a builtin config name "
+                             f"(builtin: {', '.join(sorted(BUILTIN))})")
         spec = replace(BUILTIN[args.cfg], score_thresh=args.min_score)
         if args.nms_thresh is not None:
             spec = replace(spec, nms_test=args.nms_thresh)

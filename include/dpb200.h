@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DPB200_ABI_VERSION 3
+#define DPB200_ABI_VERSION 4
 
 const char* dpb200_last_error(void);
 int dpb200_abi_version(void);
@@ -83,14 +83,24 @@ int dpb200_conv2d(const dpb200_conv2d_args* a, void* stream);
  * scale_factor=k) fused with GeneralizedRCNN.preprocess_image (meta_arch/rcnn.py:156-181: normalise,
  * zero-pad to /32).  src [B,H0,W0,3] HWC fp32 (or u8); dst = space-to-depth stem layout [B,Hp/2,Wx,16] bf16:
  * padded-image pixel (y,x,c) at [y/2][x/2+2][((y&1)*2+(x&1))*4+c], Wx = Wp/2+4, channel 3 of each sub-pixel and
- * everything outside the resized image is 0 (on it the 7x7/2 stem conv is a 4x4/1 conv over 16 channels). */
+ * everything outside the resized image is 0 (on it the 7x7/2 stem conv is a 4x4/1 conv over 16 channels).
+ * Both input types reproduce ATen's CPU kernels bit for bit: fp32 through its FMA-contracted float bilinear
+ * (variant 0: the separable kernel a multi-threaded reference runs; 1: the channels-last kernel a single-threaded
+ * one runs for a 3-channel image), u8 (what run.py:33-36 feeds) through its int16 fixed-point two-pass scheme,
+ * whose per-axis weight tables dpb200_u8_resize_tables builds on the device. */
 typedef struct dpb200_preprocess_args {
   const void* src; int32_t src_u8; int32_t b, h0, w0;
   int32_t hr, wr; float inv_scale; int32_t flip_rgb;
   float mean[3]; float std[3];
   void* dst; int32_t hp, wx;
+  const void* tables;       /* u8 input: (1 + hr + wr) * 8 bytes filled by dpb200_u8_resize_tables; else NULL */
+  int32_t variant;          /* fp32 input: 0 | 1 (see above)                                              */
+  void* dst_lo;             /* strict numerics: low half of the bf16 hi/lo split of dst, else NULL        */
 } dpb200_preprocess_args;
 int dpb200_preprocess(const dpb200_preprocess_args* a, void* stream);
+/* ATen's uint8 upsample_bilinear2d weights (UpSampleKernelAVXAntialias.h scheme: double-precision centres
+ * scale*(i+0.5), scale = 1.0/k, int16 weights at the largest precision that keeps them below 2^15), both axes. */
+int dpb200_u8_resize_tables(void* tables, int32_t h0, int32_t hr, int32_t w0, int32_t wr, double scale, void* stream);
 
 /* F.max_pool2d(k=3,s=2,p=1) of BasicStem.forward (backbone/resnet.py:353). NHWC bf16. */
 int dpb200_maxpool3x3s2(const void* x, void* y, int32_t b, int32_t h, int32_t w, int32_t c, void* stream);
@@ -146,9 +156,10 @@ int dpb200_groupnorm_relu(const void* x, const float* gamma, const float* beta, 
 int dpb200_avgpool(const void* x, void* y, int32_t r, int32_t hw, int32_t c, const int32_t* n_valid, void* stream);
 
 /* interp2d (bilinear x2) of DensePoseChartPredictor.forward (densepose/modeling/predictors/chart.py:62-90).
- * low [R,S,S,cpad] fp32 NHWC (coarse[kc], fine[25], u[25], v[25]) -> four NCHW fp32 [R,C,2S,2S].
- * planar != 0: low is [R,2,2,cpad,S/2,S/2] — the four ConvTranspose output phases (py,px) as channel planes,
- * the layout dpb200_conv2d writes with y_sc > 1. */
+ * low [R,2,2,cpad,S/2,S/2] fp32 — the four ConvTranspose output phases (py,px) as channel planes (channels
+ * coarse[kc], fine[25], u[25], v[25]), the layout dpb200_conv2d writes with y_sc > 1 — -> four NCHW fp32
+ * [R,C,2S,2S]. planar must be 1 (the NHWC variant of ABI 3 is gone). Bit-identical to ATen's CPU bilinear,
+ * including its switch to the channels-last kernel when the output h + w <= 128 (the legacy 56x56 heads). */
 int dpb200_predictor_upsample(const float* low, int32_t r, int32_t s, int32_t cpad, int32_t kc,
                               const int32_t* n_valid, float* coarse, float* fine, float* u, float* v,
                               int32_t planar, void* stream);

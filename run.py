@@ -32,7 +32,7 @@ def main():
     predictor = predictor.cuda()
     predictor = predictor.float() if args.fp32 else predictor.half()      # run.py:20-29
 
-    visualizer = End2EndVisualizer(alpha=.7, inplace=True)
+    visualizer = End2EndVisualizer(alpha=.7, keep_bg=False)         # run.py:17
     save_path = "_pred".join(os.path.splitext(args.input))
     img = cv2.imread(args.input)
     if img is not None:

@@ -23,7 +23,18 @@ from oracle import weights as W  # noqa: E402
 CONFIGS = ["densepose_rcnn_R_50_FPN_s1x_legacy", "densepose_rcnn_R_50_FPN_s1x", "densepose_rcnn_R_101_FPN_DL_s1x",
            "densepose_rcnn_R_50_FPN_DL_s1x", "densepose_rcnn_R_101_FPN_s1x", "densepose_rcnn_R_101_FPN_s1x_legacy"]
 IMAGE = dict(height=240, width=600, seed=3)
+# extra fixtures (name -> (config, image, uint8 input)): the uint8 image path of run.py:33-36 (ATen resizes uint8 in
+# fixed point) and the two benchmarked shapes at full size (BASELINE configs[1] and configs[3])
+EXTRA = {
+    "densepose_rcnn_R_50_FPN_s1x__u8": ("densepose_rcnn_R_50_FPN_s1x", dict(height=240, width=600, seed=3), True),
+    "densepose_rcnn_R_50_FPN_s1x_legacy__u8": ("densepose_rcnn_R_50_FPN_s1x_legacy", dict(height=240, width=600, seed=3), True),
+    "densepose_rcnn_R_50_FPN_s1x__800x1333": ("densepose_rcnn_R_50_FPN_s1x", dict(height=800, width=1333, seed=1), False),
+    "densepose_rcnn_R_101_FPN_s1x__1080p": ("densepose_rcnn_R_101_FPN_s1x", dict(height=1080, width=1920, seed=11), False),
+    "densepose_rcnn_R_101_FPN_s1x__1080p_u8": ("densepose_rcnn_R_101_FPN_s1x", dict(height=1080, width=1920, seed=11), True),
+}
 DP_KEYS = ["pred_densepose_coarse_segm", "pred_densepose_fine_segm", "pred_densepose_u", "pred_densepose_v"]
+N_LABELS = 16      # detections whose native-resolution part-label map is stored
+N_SAMPLE = 8       # detections whose strided DensePose samples are stored (fp16)
 
 
 def build_reference(name: str):
@@ -40,6 +51,19 @@ def build_reference(name: str):
     return DefaultPredictor(cfg)
 
 
+def make_image(image: dict, u8: bool):
+    """The seeded synthetic image; u8: rounded to uint8 HWC, what cv2.imread hands run.py:33-36."""
+    img = W.synthetic_image(**image)
+    return img.round().clamp(0, 255).to(torch.uint8) if u8 else img
+
+
+def label_map(out, n):
+    """Native-resolution (4S x 4S) part labels of the first n detections: argmax25(fine) * (argmaxK(coarse) > 0)."""
+    fine = out["pred_densepose_fine_segm"][:n].argmax(1)
+    fg = out["pred_densepose_coarse_segm"][:n].argmax(1) > 0
+    return (fine * fg).to(torch.uint8)
+
+
 def summarize(out):
     fx = {"pred_boxes": out["pred_boxes"].clone(), "scores": out["scores"].clone(),
           "pred_classes": out["pred_classes"].clone(), "image_size": out["image_size"].clone()}
@@ -49,32 +73,46 @@ def summarize(out):
         fx[k + ".sum"] = float(t.double().sum())
         fx[k + ".abssum"] = float(t.double().abs().sum())
         fx[k + ".sample"] = t[:4, :, ::8, ::8].clone()
+        fx[k + ".sample16"] = t[:N_SAMPLE, :, ::8, ::8].half()
+    fx["labels_native"] = label_map(out, N_LABELS)
     return fx
+
+
+def generate(name: str, config: str, image: dict, u8: bool, here: str):
+    spec = O.SPECS[config]
+    sd = W.make_state_dict(spec, 0)
+    pred = build_reference(config)
+    pred.load_state_dict(W.add_aliases(sd, spec), strict=True)
+    img = make_image(image, u8)
+    with torch.no_grad():
+        out = pred(img)
+    fx = summarize(out)
+    fx["config"] = config
+    fx["image"] = dict(image)
+    fx["uint8"] = u8
+    fx["torch"] = torch.__version__
+    fx["threads"] = torch.get_num_threads()        # > 1: ATen's separable float resize kernel (oracle/aten_interp.py)
+    # the visualizer's per-box extractor on the first three detections (visualizer.py:46-56)
+    from visualizer import DensePoseResultExtractor
+    sub = {k: (v[:3] if k != "image_size" else v) for k, v in out.items()}
+    results, _ = DensePoseResultExtractor()(sub)
+    fx["extract.labels"] = [r["labels"].to(torch.uint8) for r in results]
+    fx["extract.uv_sum"] = [float(r["uv"].double().sum()) for r in results]
+    path = os.path.join(here, name + ".pt")
+    torch.save(fx, path)
+    print(name, "detections", len(out["scores"]), "->", path, os.path.getsize(path) // 1024, "KiB")
 
 
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
-    for name in (sys.argv[1:] or CONFIGS):
-        spec = O.SPECS[name]
-        sd = W.make_state_dict(spec, 0)
-        pred = build_reference(name)
-        pred.load_state_dict(W.add_aliases(sd, spec), strict=True)
-        img = W.synthetic_image(**IMAGE)
-        with torch.no_grad():
-            out = pred(img)
-        fx = summarize(out)
-        fx["config"] = name
-        fx["image"] = dict(IMAGE)
-        fx["torch"] = torch.__version__
-        # the visualizer's per-box extractor on the first three detections (visualizer.py:46-56)
-        from visualizer import DensePoseResultExtractor
-        sub = {k: (v[:3] if k != "image_size" else v) for k, v in out.items()}
-        results, _ = DensePoseResultExtractor()(sub)
-        fx["extract.labels"] = [r["labels"].to(torch.uint8) for r in results]
-        fx["extract.uv_sum"] = [float(r["uv"].double().sum()) for r in results]
-        path = os.path.join(here, name + ".pt")
-        torch.save(fx, path)
-        print(name, "detections", len(out["scores"]), "->", path, os.path.getsize(path) // 1024, "KiB")
+    assert torch.get_num_threads() > 1, "generate with > 1 intra-op threads (the float resize kernel depends on it)"
+    todo = sys.argv[1:] or (CONFIGS + list(EXTRA))
+    for name in todo:
+        if name in EXTRA:
+            config, image, u8 = EXTRA[name]
+            generate(name, config, image, u8, here)
+        else:
+            generate(name, name, IMAGE, False, here)
 
 
 if __name__ == "__main__":

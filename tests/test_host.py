@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(_lib.lib, name), f"{name} is declared in dpb200.h but not exported by libdpb200.so"
     assert declared == set(_lib.EXPORTS)
-    assert _lib.lib.dpb200_abi_version() == 3
+    assert _lib.lib.dpb200_abi_version() == 4
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     for name in declared:
         assert re.search(rf"\bT {name}\b", out), name
@@ -72,6 +72,50 @@ def test_yaml_reader_on_reference_configs():
         assert y == spec, name
     wc = spec_from_yaml(os.path.join(REFERENCE, "configs", "densepose_rcnn_R_50_FPN_WC1_s1x.yaml"), min_score=0.5, nms_thresh=0.4)
     assert (wc.head, wc.decoder_on, wc.pooler_res, wc.score_thresh, wc.nms_test) == ("v1convx", True, 28, 0.5, 0.4)
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference yaml files not present")
+def test_yaml_reader_rejects_what_the_engine_does_not_compute():
+    """Keys that change the numerics are validated, not ignored: CSE / HRNet / evolution yamls (other predictor,
+    backbone, ROI heads or ROIAlignV2 poolers) raise instead of exporting a model that computes something else;
+    WC* yamls are read with their confidence heads recorded."""
+    from densepose_torchscript_b200.config import spec_from_yaml
+    cfgs = os.path.join(REFERENCE, "configs")
+    for bad, why in (("cse/densepose_rcnn_R_50_FPN_s1x.yaml", "PREDICTOR_NAME"),
+                     ("HRNet/densepose_rcnn_HRFPN_HRNet_w32_s1x.yaml", "BACKBONE"),
+                     ("evolution/densepose_R_50_FPN_DL_WC1M_3x_Atop10P_CA.yaml", "POOLER_TYPE")):
+        with pytest.raises(ValueError, match=why):
+            spec_from_yaml(os.path.join(cfgs, bad))
+    with pytest.raises(FileNotFoundError, match="builtin names"):
+        spec_from_yaml(os.path.join(cfgs, "densepose_rcnn_R_50_FPN_s1x_typo.yaml"))
+    wc2m = spec_from_yaml(os.path.join(cfgs, "densepose_rcnn_R_50_FPN_WC2M_s1x.yaml"))
+    assert (wc2m.uv_confidence, wc2m.segm_confidence) == ("indep_aniso", True)
+    wc1 = spec_from_yaml(os.path.join(cfgs, "densepose_rcnn_R_101_FPN_DL_WC1_s1x.yaml"))
+    assert (wc1.uv_confidence, wc1.segm_confidence, wc1.head, wc1.depth) == ("iid_iso", False, "deeplab", 101)
+
+
+@pytest.mark.skipif(not have_reference(), reason="the reference visualizer is not present")
+def test_visualizer_draws_exactly_like_the_reference():
+    """End2EndVisualizer.draw == the reference's DensePoseResultsFineSegmentationVisualizer (visualizer.py:96-129) on
+    the same extracted results: VIRIDIS, alpha blend per box, and the whole-frame fill of keep_bg=False (run.py:17)."""
+    import importlib.util
+    import cv2
+    from densepose_torchscript_b200.extractor import End2EndVisualizer
+    spec = importlib.util.spec_from_file_location("ref_visualizer", os.path.join(REFERENCE, "visualizer.py"))
+    RV = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(RV)
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (200, 320, 3), dtype=torch.uint8, generator=g).numpy()
+    boxes = torch.tensor([[10.2, 20.7, 150.9, 190.1], [0., 0., 0.4, 0.3], [5.5, 5.5, 260., 90.2], [100., 50., 131.9, 199.]])
+    inst = {"pred_boxes": boxes, "pred_densepose_coarse_segm": torch.randn(4, 2, 112, 112, generator=g),
+            "pred_densepose_fine_segm": torch.randn(4, 25, 112, 112, generator=g),
+            "pred_densepose_u": torch.rand(4, 25, 112, 112, generator=g), "pred_densepose_v": torch.rand(4, 25, 112, 112, generator=g)}
+    results, xywh = RV.DensePoseResultExtractor()(inst)
+    for keep_bg in (True, False):
+        want = RV.End2EndVisualizer(alpha=.7, keep_bg=keep_bg).visualize(img.copy(), inst)
+        ours = End2EndVisualizer(alpha=.7, keep_bg=keep_bg)
+        assert ours.cmap == cv2.COLORMAP_VIRIDIS
+        assert np.array_equal(ours.draw(img.copy(), results, xywh), want)
 
 
 # ------------------------------------------------------------------------------------------- weight packer
