@@ -40,6 +40,7 @@ class Conv2dArgs(C.Structure):
         ("y", vp), ("y_fp32", i32), ("y_sn", i64), ("y_sy", i64), ("y_sx", i64),
         ("n_valid", vp), ("block_n", i32), ("stages", i32), ("tiled", i32),
         ("y_sc", i64), ("epilogue", i32), ("ks", i32), ("phase_taps", i32), ("pair", i32),
+        ("x_lo", vp), ("res_lo", vp), ("y_lo", vp),
     ]
 
 
@@ -91,7 +92,7 @@ class ModelConfig(C.Structure):
         ("score_thresh", f32), ("nms_test", f32), ("rpn_nms", f32),
         ("dets_per_image", i32), ("rpn_pre_topk", i32), ("rpn_post_topk", i32),
         ("min_size", i32), ("max_size", i32),
-        ("pixel_mean", f32 * 3), ("pixel_std", f32 * 3), ("input_rgb", i32),
+        ("pixel_mean", f32 * 3), ("pixel_std", f32 * 3), ("input_rgb", i32), ("strict", i32),
     ]
 
 

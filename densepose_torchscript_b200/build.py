@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["conv_igemm.cu", "elementwise.cu", "rpn.cu", "roi.cu", "resample.cu", "engine.cu", "api.cu"]
+SOURCES = ["conv_igemm.cu", "elementwise.cu", "rpn.cu", "roi.cu", "resample.cu", "strict.cu", "engine.cu", "api.cu"]
 OUT = os.path.join(HERE, "libdpb200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -52,6 +52,7 @@ int dpb200_conv2d(const dpb200_conv2d_args* a, void* stream) {
   d.im2col = a->tiled ? 0 : 1;
   d.out_sc = a->y_sc > 0 ? a->y_sc : 1;
   d.epilogue = a->epilogue;
+  d.x2 = a->x_lo; d.res2 = a->res_lo; d.out2 = a->y_lo;
   dpb::ConvPlan plan;
   int r = dpb::conv_plan_build(&plan, d, num_sms());
   if (r) return r;

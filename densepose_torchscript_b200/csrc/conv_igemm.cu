@@ -87,7 +87,7 @@ template <bool kStaged, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
-                  const ConvKParams p) {
+                  const __grid_constant__ CUtensorMap tmA2, const ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // warp index made provably warp-uniform, so the role loops below compile to uniform-datapath code
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -119,6 +119,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (p.nseg > 1) prefetch_tmap(&tmA2);
     if (kStaged) {
       prefetch_tmap(&tmOut);
       if (p.res_tma) prefetch_tmap(&tmRes);
@@ -162,7 +163,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int total_tiles = (kPair ? (m_tiles + 1) >> 1 : m_tiles) * p.n_blocks;
   const int t_begin = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int t_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int k_iters = p.kh * p.kw * p.cin_chunks;
+  const int k_iters = p.kh * p.kw * p.cin_chunks * p.nseg;
   const uint32_t a_tx = p.im2col ? (uint32_t)kABytes : (uint32_t)(p.tw * p.th * p.tn) * 128u;
   const int hw_out = p.H_out * p.W_out;
   const int m_valid = nvalid * hw_out;
@@ -206,38 +207,43 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int b_row = n_blk * block_n + (kPair ? (int)rank * (block_n >> 1) : 0);
       // deconv phases: block (py,px) = (n_blk >> 1, n_blk & 1) starts its 2x2 taps at (py,px) of the 3x3 footprint
       const int pyo = p.phase_taps ? (n_blk >> 1) * dil : 0, pxo = p.phase_taps ? (n_blk & 1) * dil : 0;
-      int cc = 0, kx = 0, ky = 0, kcol = 0;
+      // K order per tap: cin chunks fastest, then the strict-mode segment (hi*w_hi, hi*w_lo, lo*w_hi), then (kx, ky);
+      // the weight matrix is packed in exactly this order, so its column just advances by 64 per chunk
+      int cc = 0, seg = 0, kx = 0, ky = 0, kcol = 0;
+      const int nseg = p.nseg;
+      auto advance = [&]() {
+        if (++cc == cin_chunks) { cc = 0; if (++seg == nseg) { seg = 0; if (++kx == kw) { kx = 0; ++ky; } } }
+        kcol += 64;
+      };
       for (int g = 0; g < n_groups; ++g) {
         mbar_wait(bar_base + 8u * (uint32_t)(n_stages + s), ph ^ 1u);           // empty[s]
         const int nsub = (ks == 2 && g * 2 + 1 < k_iters) ? 2 : 1;
         // coordinates of the (up to) two chunks of this group, computed by the whole warp
         const int c0 = cc * 64, ox0 = kx * dil + pxo, oy0 = ky * dil + pyo, kc0 = kcol;
-        if (++cc == cin_chunks) { cc = 0; if (++kx == kw) { kx = 0; ++ky; } }
-        kcol += 64;
+        const CUtensorMap* tm0 = seg == 2 ? &tmA2 : &tmA;
+        advance();
         const int c1 = cc * 64, ox1 = kx * dil + pxo, oy1 = ky * dil + pyo, kc1 = kcol;
-        if (nsub == 2) {
-          if (++cc == cin_chunks) { cc = 0; if (++kx == kw) { kx = 0; ++ky; } }
-          kcol += 64;
-        }
+        const CUtensorMap* tm1 = seg == 2 ? &tmA2 : &tmA;
+        if (nsub == 2) advance();
         if (kPair) {
           if (elect_one()) {
             const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
             const uint32_t fb = bar_base + 8u * (uint32_t)s;                      // full[s]
             if (rank == 0) mbar_expect_tx(fb, 2u * (a_tx + b_bytes));             // both CTAs' bytes land here
             const uint32_t fb0 = mapa_shared(fb, 0);
-            tma_load_im2col_4d_pair(a_dst, &tmA, fb0, c0, ix0, iy0, in0, (uint16_t)ox0, (uint16_t)oy0);
+            tma_load_im2col_4d_pair(a_dst, tm0, fb0, c0, ix0, iy0, in0, (uint16_t)ox0, (uint16_t)oy0);
             tma_load_2d_pair(a_dst + kABytes, &tmB, fb0, kc0, b_row);
           }
         } else if (elect_one()) {
           const uint32_t a_dst = smem_base + (uint32_t)(s * ks) * stage_bytes;
           const uint32_t fb = bar_base + 8u * (uint32_t)s;                        // full[s]
           mbar_expect_tx(fb, (uint32_t)nsub * (a_tx + b_bytes));
-          if (im2col) tma_load_im2col_4d(a_dst, &tmA, fb, c0, ix0, iy0, in0, (uint16_t)ox0, (uint16_t)oy0);
-          else tma_load_4d(a_dst, &tmA, fb, c0, ix0 + ox0, iy0 + oy0, in0);
+          if (im2col) tma_load_im2col_4d(a_dst, tm0, fb, c0, ix0, iy0, in0, (uint16_t)ox0, (uint16_t)oy0);
+          else tma_load_4d(a_dst, tm0, fb, c0, ix0 + ox0, iy0 + oy0, in0);
           tma_load_2d(a_dst + kABytes, &tmB, fb, kc0, b_row);
           if (nsub == 2) {
-            if (im2col) tma_load_im2col_4d(a_dst + stage_bytes, &tmA, fb, c1, ix0, iy0, in0, (uint16_t)ox1, (uint16_t)oy1);
-            else tma_load_4d(a_dst + stage_bytes, &tmA, fb, c1, ix0 + ox1, iy0 + oy1, in0);
+            if (im2col) tma_load_im2col_4d(a_dst + stage_bytes, tm1, fb, c1, ix0, iy0, in0, (uint16_t)ox1, (uint16_t)oy1);
+            else tma_load_4d(a_dst + stage_bytes, tm1, fb, c1, ix0 + ox1, iy0 + oy1, in0);
             tma_load_2d(a_dst + stage_bytes + kABytes, &tmB, fb, kc1, b_row);
           }
         }
@@ -503,9 +509,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const long long out_off = on * p.out_sn + oy * p.out_sy + ox * p.out_sx + c_base;
       const long long out_off_planar = on * p.out_sn + oy * p.out_sy + ox * p.out_sx + (long long)c_base * p.out_sc;
       const __nv_bfloat16* res_ptr = nullptr;
+      const __nv_bfloat16* res2_ptr = nullptr;
       if (p.res != nullptr && valid) {
-        res_ptr = p.res + on * p.res_sn + (long long)(oy >> p.res_shift) * p.res_sy +
-                  (long long)(ox >> p.res_shift) * p.res_sx + c_base;
+        const long long ro = on * p.res_sn + (long long)(oy >> p.res_shift) * p.res_sy +
+                             (long long)(ox >> p.res_shift) * p.res_sx + c_base;
+        res_ptr = p.res + ro;
+        if (p.res2 != nullptr) res2_ptr = p.res2 + ro;
       }
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
@@ -527,7 +536,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               f[4 * i + 0] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
             }
           }
-          if (res_ptr != nullptr) {
+          if (res2_ptr != nullptr) {
+            // strict mode: the residual is hi + lo (exact in fp32), added once like the reference's fp32 add
+            const uint4* r4 = reinterpret_cast<const uint4*>(res_ptr + c0);
+            const uint4* l4 = reinterpret_cast<const uint4*>(res2_ptr + c0);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const uint4 r = __ldg(r4 + i), l = __ldg(l4 + i);
+              f[8 * i + 0] += bf16_lo(r.x) + bf16_lo(l.x); f[8 * i + 1] += bf16_hi(r.x) + bf16_hi(l.x);
+              f[8 * i + 2] += bf16_lo(r.y) + bf16_lo(l.y); f[8 * i + 3] += bf16_hi(r.y) + bf16_hi(l.y);
+              f[8 * i + 4] += bf16_lo(r.z) + bf16_lo(l.z); f[8 * i + 5] += bf16_hi(r.z) + bf16_hi(l.z);
+              f[8 * i + 6] += bf16_lo(r.w) + bf16_lo(l.w); f[8 * i + 7] += bf16_hi(r.w) + bf16_hi(l.w);
+            }
+          } else if (res_ptr != nullptr) {
             const uint4* r4 = reinterpret_cast<const uint4*>(res_ptr + c0);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -555,6 +576,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           } else {
             uint4* o4 =
                 reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + c0);
+            uint4* l4 = p.out2 == nullptr ? nullptr :
+                reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + out_off + c0);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               uint4 o;
@@ -563,6 +586,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               o.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
               o.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
               o4[i] = o;
+              if (l4 != nullptr) {            // strict mode: lo = bf16(x - hi)
+                uint4 l;
+                l.x = pack_bf16(f[8 * i + 0] - bf16_lo(o.x), f[8 * i + 1] - bf16_hi(o.x));
+                l.y = pack_bf16(f[8 * i + 2] - bf16_lo(o.y), f[8 * i + 3] - bf16_hi(o.y));
+                l.z = pack_bf16(f[8 * i + 4] - bf16_lo(o.z), f[8 * i + 5] - bf16_hi(o.z));
+                l.w = pack_bf16(f[8 * i + 6] - bf16_lo(o.w), f[8 * i + 7] - bf16_hi(o.w));
+                l4[i] = l;
+              }
             }
           }
         }
@@ -743,6 +774,12 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
   p.kh = d.kh; p.kw = d.kw; p.sx = d.sx; p.sy = d.sy; p.pad_x = d.pad_x; p.pad_y = d.pad_y;
   p.dil = d.dil;
   p.phase_taps = d.phase_taps;
+  const bool strict = d.x2 != nullptr;
+  p.nseg = strict ? 3 : 1;
+  p.res2 = reinterpret_cast<const __nv_bfloat16*>(d.res2);
+  p.out2 = d.out2;
+  if (strict && d.res != nullptr && d.res2 == nullptr) { set_error("conv: strict mode needs both halves of the residual"); return -1; }
+  if (strict && !d.out_fp32 && d.out2 == nullptr) { set_error("conv: strict mode needs both halves of a bf16 output"); return -1; }
   p.cin_chunks = d.cin_pad / 64;
   p.relu = d.relu; p.out_fp32 = d.out_fp32; p.res_shift = d.res_shift;
   p.bias = d.bias;
@@ -753,7 +790,7 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
   p.n_valid = d.n_valid;
   if (p.out_sc != 1 && !d.out_fp32) { set_error("conv: planar output must be fp32"); return -1; }
 
-  const int k_iters = d.kh * d.kw * p.cin_chunks;
+  const int k_iters = d.kh * d.kw * p.cin_chunks * p.nseg;
   const long long m_total = (long long)d.N * d.H_out * d.W_out;
   // Staged epilogue (smem slabs + TMA): bf16 output that is a plain [M, C] matrix (row stride out_sx) in
   // im2col row order. Measured faster than direct stores for every shape on the path (3x on the K=64 1x1
@@ -761,7 +798,7 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
   const bool out_matrix = d.im2col && !d.out_fp32 && p.out_sc == 1 && block_n % 64 == 0 &&
                           d.out_sy == d.out_sx * d.W_out && d.out_sn == d.out_sy * d.H_out &&
                           d.out_sx % 8 == 0 && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0;
-  bool staged = out_matrix && d.epilogue != 1;
+  bool staged = out_matrix && d.epilogue != 1 && !strict;     // strict mode writes two tensors: direct stores
   if (d.epilogue == 2 && !out_matrix) { set_error("conv: staged epilogue needs a bf16 [M, C] output"); return -1; }
   const bool res_matrix = d.res != nullptr && d.res_shift == 0 && d.res_sy == d.res_sx * d.W_out &&
                           d.res_sn == d.res_sy * d.H_out && d.res_sx % 8 == 0 &&
@@ -774,7 +811,7 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
   // CTA pairs (cta_group::2): staged im2col convs whose N tile splits into two halves of a multiple of 16 rows.
   // Chosen automatically for the long-K, 256-wide tiles (the 3x3 256->256 / 512->512 convs), where halving the
   // weight traffic from L2 pays; d.pair forces it on (2) or off (1).
-  const bool pair_ok = d.im2col && block_n % 16 == 0 && block_n >= 32 && (num_sms & ~1) >= 2;
+  const bool pair_ok = d.im2col && block_n % 16 == 0 && block_n >= 32 && (num_sms & ~1) >= 2 && !strict;
   if (d.pair == 2 && !pair_ok) { set_error("conv: pair mode needs an im2col conv with block_n %% 16 == 0"); return -1; }
   // (measured on the path's shapes: short-K tiles lose to the pair's extra barrier traffic; K >= 18 chunks gains 6-10 %)
   const bool pair = d.pair == 2 || (d.pair == 0 && pair_ok && staged && block_n == 256 && k_iters >= 18 && m_total >= 4096);
@@ -826,9 +863,21 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
       r = encode_tiled_bf16(&plan->tmA, d.x, 4, dims, strides, box, estr);
     }
     if (r) return r;
+    plan->tmA2 = plan->tmA;
+    if (strict) {
+      if (d.im2col) {
+        int lower[2] = {-d.pad_x, -d.pad_y};
+        int upper[2] = {(d.W_out - 1) * d.sx - d.pad_x - (d.W - 1),
+                        (d.H_out - 1) * d.sy - d.pad_y - (d.H - 1)};
+        r = encode_im2col_bf16(&plan->tmA2, d.x2, dims, strides, lower, upper, 64, 128, estr, 1);
+      } else {
+        r = encode_tiled_bf16(&plan->tmA2, d.x2, 4, dims, strides, box, estr);
+      }
+      if (r) return r;
+    }
   }
   {
-    const uint64_t K = (uint64_t)d.kh * d.kw * d.cin_pad;
+    const uint64_t K = (uint64_t)d.kh * d.kw * p.nseg * d.cin_pad;
     uint64_t dims[2] = {K, (uint64_t)d.cout_pad};
     uint64_t strides[1] = {K * 2};
     uint32_t box[2] = {64, (uint32_t)b_rows};
@@ -910,13 +959,13 @@ int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
   cfg.numAttrs = (unsigned)na;
   cudaError_t le;
   if (plan.pair && plan.staged)
-    le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, true>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.p);
+    le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, true>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.tmA2, plan.p);
   else if (plan.pair)
-    le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, true>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.p);
+    le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, true>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.tmA2, plan.p);
   else if (plan.staged)
-    le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, false>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.p);
+    le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, false>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.tmA2, plan.p);
   else
-    le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, false>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.p);
+    le = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, false>, plan.tmA, plan.tmB, plan.tmOut, plan.tmRes, plan.tmA2, plan.p);
   if (le != cudaSuccess) { set_error("conv launch: %s", cudaGetErrorString(le)); return -4; }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv launch: %s", cudaGetErrorString(e)); return -4; }

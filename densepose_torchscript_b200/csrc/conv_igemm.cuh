@@ -41,6 +41,13 @@ struct ConvDesc {
   // so the four CTAs working on one pixel tile share the same input rows through L2.
   int phase_taps = 0;
   int pair = 0;                                   // CTA pairs (cta_group::2, weights split over the pair): 0 choose, 1 off, 2 on
+  // Strict (fp32-class) numerics: every activation is a PAIR of bf16 tensors (hi, lo) with x = hi + lo
+  // (hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits), weights likewise, packed per tap as three K segments
+  // [w_hi | w_lo | w_hi]; the K loop then runs x_hi*w_hi + x_hi*w_lo + x_lo*w_hi into the same fp32 TMEM
+  // accumulator (three tcgen05.mma passes, the lo*lo term of relative size 2^-18 is dropped).
+  const void* x2 = nullptr;                       // lo half of the input (same strides as x); non-null selects the mode
+  const void* res2 = nullptr;                     // lo half of the residual
+  void* out2 = nullptr;                           // lo half of a bf16 output (same strides as out)
 };
 
 struct ConvKParams {
@@ -54,6 +61,9 @@ struct ConvKParams {
   int nslab, res_tma;                             // staged epilogue: slab ring size, residual through TMA
   int relu, out_fp32, res_shift, im2col;
   int phase_taps;
+  int nseg;                                       // K segments per tap: 1, or 3 in strict mode (x_hi*w_hi, x_hi*w_lo, x_lo*w_hi)
+  const __nv_bfloat16* res2;
+  void* out2;
   const float* bias;
   const __nv_bfloat16* res;
   long long res_sn, res_sy, res_sx;
@@ -64,6 +74,7 @@ struct ConvKParams {
 
 struct ConvPlan {
   alignas(64) CUtensorMap tmA;
+  alignas(64) CUtensorMap tmA2;    // strict mode: the lo half of the input (else a copy of tmA)
   alignas(64) CUtensorMap tmB;
   alignas(64) CUtensorMap tmOut;   // staged epilogue: [M, cout] bf16 view of the output
   alignas(64) CUtensorMap tmRes;   // staged epilogue: [M, cout] bf16 view of the residual

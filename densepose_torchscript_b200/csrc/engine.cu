@@ -83,15 +83,18 @@ struct Builder {
     if (s->ws_used > s->ws_bytes) { fail = -10; set_error("session: workspace too small"); return nullptr; }
     return s->ws + off;
   }
+  bool strict() const { return m->cfg.strict != 0; }
   T4 act(int N, int H, int W, int C, int fp32 = 0) {
     T4 t; t.N = N; t.H = H; t.W = W; t.C = C; t.fp32 = fp32;
     t.p = alloc((size_t)t.elems() * (fp32 ? 4 : 2));
+    if (strict() && !fp32) t.p2 = alloc((size_t)t.elems() * 2);     // bf16 activations are hi/lo pairs
     return t;
   }
   void tap(const std::string& name, const T4& t) {
     TensorInfo ti; ti.p = t.p; ti.shape[0] = t.N; ti.shape[1] = t.H; ti.shape[2] = t.W; ti.shape[3] = t.C;
     ti.dtype = t.fp32 ? 1 : 0;
     s->taps[name] = ti;
+    if (t.p2) { ti.p = t.p2; s->taps[name + ".lo"] = ti; }      // strict mode: value = tap(name) + tap(name + ".lo")
   }
   void tap_raw(const std::string& name, void* p, int64_t a, int64_t b, int64_t c, int64_t d, int dtype) {
     TensorInfo ti; ti.p = p; ti.shape[0] = a; ti.shape[1] = b; ti.shape[2] = c; ti.shape[3] = d; ti.dtype = dtype;
@@ -146,11 +149,17 @@ struct Builder {
     d.out_sc = o.out_sc ? o.out_sc : 1;
     d.out = y.fp32 ? (void*)(reinterpret_cast<float*>(y.p) + o.out_off)
                    : (void*)(reinterpret_cast<bf16*>(y.p) + o.out_off);
+    if (strict()) {
+      d.x2 = x.p2;
+      if (!d.x2) { fail = -13; set_error("conv %s: strict mode input has no lo half", wname.c_str()); return; }
+      if (o.res) d.res2 = o.res->p2;
+      if (!y.fp32) d.out2 = (void*)(reinterpret_cast<bf16*>(y.p2) + o.out_off);
+    }
     d.n_valid = o.n_valid;
     d.phase_taps = o.phase_taps;
     d.pair = o.pair;
     if (d.cout_pad > y.C && !o.out_sx) { fail = -12; set_error("conv %s: output has %d channels, weights %d", wname.c_str(), y.C, d.cout_pad); return; }
-    const double fl = 2.0 * x.N * d.H_out * d.W_out * (double)w->cout_pad * d.kh * d.kw * w->cin_pad;
+    const double fl = 2.0 * x.N * d.H_out * d.W_out * (double)w->cout_pad * d.kh * d.kw * w->cin_pad * (strict() ? 3 : 1);
     s->flops += fl;
     s->op_names.push_back("conv:" + wname);
     s->op_flops.push_back(fl);
@@ -246,9 +255,11 @@ int build_plan(dpb200_session* s) {
     b.conv("backbone.bottom_up.stem.conv1", xv, stem, o);
   }
   T4 pool = b.act(B, Hp / 4, Wp / 4, 64);
+  const bool strict = b.strict();
   b.op([=](cudaStream_t st) {
+    if (strict) return launch_maxpool3x3s2_split((const bf16*)stem.p, (const bf16*)stem.p2, (bf16*)pool.p, (bf16*)pool.p2, B, stem.H, stem.W, 64, st);
     return launch_maxpool3x3s2((const bf16*)stem.p, (bf16*)pool.p, B, stem.H, stem.W, 64, st);
-  }, "maxpool3x3s2", (double)stem.elems() * 2 + (double)pool.elems() * 2);
+  }, "maxpool3x3s2", ((double)stem.elems() * 2 + (double)pool.elems() * 2) * (strict ? 2 : 1));
   b.tap("stem_pool", pool);
 
   // ---- a4 res2..res5
@@ -351,8 +362,11 @@ int build_plan(dpb200_session* s) {
     RoiAlignArgs a{};
     for (int l = 0; l < 4; ++l) { a.feat[l] = (const bf16*)pf[l].p; a.H[l] = pf[l].H; a.W[l] = pf[l].W; a.scale[l] = 1.0f / (float)(4 << l); }
     a.n_levels = 4; a.C = 256; a.rois = rois_box; a.n_rois = nullptr; a.R = B * R; a.P = 7; a.out = box_pooled.p; a.out_fp32 = 0;
-    b.op([a](cudaStream_t st) { return launch_roi_align(a, st); }, "roi_align_box",
-         (double)(pf[0].elems() + pf[1].elems() + pf[2].elems() + pf[3].elems()) * 2 + (double)box_pooled.elems() * 2);
+    RoiAlignSplit sp{};
+    for (int l = 0; l < 4; ++l) sp.feat_lo[l] = (const bf16*)pf[l].p2;
+    sp.out_lo = box_pooled.p2;
+    b.op([a, sp, strict](cudaStream_t st) { return strict ? launch_roi_align_split(a, sp, st) : launch_roi_align(a, st); }, "roi_align_box",
+         ((double)(pf[0].elems() + pf[1].elems() + pf[2].elems() + pf[3].elems()) * 2 + (double)box_pooled.elems() * 2) * (strict ? 2 : 1));
   }
   b.tap("box_pooled", box_pooled);
   T4 fc_in = box_pooled; fc_in.H = 1; fc_in.W = 1; fc_in.C = 7 * 7 * 256;
@@ -407,8 +421,10 @@ int build_plan(dpb200_session* s) {
         b.conv("roi_heads.decoder.p" + std::to_string(l + 2) + "." + std::to_string(2 * kk), x, y, o);
         if (kk != l - 1) {
           T4 up = b.act(B, y.H * 2, y.W * 2, 256);
-          b.op([=](cudaStream_t st) { return launch_upsample2x((const bf16*)y.p, (bf16*)up.p, B, y.H, y.W, 256, st); }, "upsample2x",
-               (double)y.elems() * 2 + (double)up.elems() * 2);
+          b.op([=](cudaStream_t st) {
+            if (strict) return launch_upsample2x_split((const bf16*)y.p, (const bf16*)y.p2, (bf16*)up.p, (bf16*)up.p2, B, y.H, y.W, 256, st);
+            return launch_upsample2x((const bf16*)y.p, (bf16*)up.p, B, y.H, y.W, 256, st);
+          }, "upsample2x", ((double)y.elems() * 2 + (double)up.elems() * 2) * (strict ? 2 : 1));
           x = up;
         } else {
           x = y;   // the last upsample is fused into the merge
@@ -418,9 +434,17 @@ int build_plan(dpb200_session* s) {
     }
     T4 merged = b.act(B, pf[0].H, pf[0].W, 256);
     b.op([=](cudaStream_t st) {
+      if (strict) {
+        const bf16* a_[2] = {(const bf16*)d2.p, (const bf16*)d2.p2};
+        const bf16* b3[2] = {(const bf16*)branch[0].p, (const bf16*)branch[0].p2};
+        const bf16* b4[2] = {(const bf16*)branch[1].p, (const bf16*)branch[1].p2};
+        const bf16* b5[2] = {(const bf16*)branch[2].p, (const bf16*)branch[2].p2};
+        bf16* o_[2] = {(bf16*)merged.p, (bf16*)merged.p2};
+        return launch_decoder_merge_split(a_, b3, b4, b5, o_, B, merged.H, merged.W, 256, st);
+      }
       return launch_decoder_merge((const bf16*)d2.p, (const bf16*)branch[0].p, (const bf16*)branch[1].p,
                                   (const bf16*)branch[2].p, (bf16*)merged.p, B, merged.H, merged.W, 256, st);
-    }, "decoder_merge", (double)(d2.elems() + branch[0].elems() + branch[1].elems() + branch[2].elems() + merged.elems()) * 2);
+    }, "decoder_merge", (double)(d2.elems() + branch[0].elems() + branch[1].elems() + branch[2].elems() + merged.elems()) * 2 * (strict ? 2 : 1));
     T4 dec = b.act(B, pf[0].H, pf[0].W, 256);
     { Builder::ConvOpt o; o.k = 1; b.conv("roi_heads.decoder.predictor", merged, dec, o); }
     b.tap("decoder", dec);
@@ -435,7 +459,11 @@ int build_plan(dpb200_session* s) {
     RoiAlignArgs a{};
     for (int l = 0; l < dp_levels; ++l) { a.feat[l] = (const bf16*)dp_feat[l].p; a.H[l] = dp_feat[l].H; a.W[l] = dp_feat[l].W; a.scale[l] = 1.0f / (float)(4 << l); }
     a.n_levels = dp_levels; a.C = 256; a.rois = s->rois_dp; a.n_rois = nv; a.R = Rd; a.P = P; a.out = dp_pooled.p;
-    b.op([a](cudaStream_t st) { return launch_roi_align(a, st); }, "roi_align_dp", (double)dp_feat[0].elems() * 2 * dp_levels + (double)dp_pooled.elems() * 2);
+    RoiAlignSplit sp{};
+    for (int l = 0; l < dp_levels; ++l) sp.feat_lo[l] = (const bf16*)dp_feat[l].p2;
+    sp.out_lo = dp_pooled.p2;
+    b.op([a, sp, strict](cudaStream_t st) { return strict ? launch_roi_align_split(a, sp, st) : launch_roi_align(a, st); }, "roi_align_dp",
+         ((double)dp_feat[0].elems() * 2 * dp_levels + (double)dp_pooled.elems() * 2) * (strict ? 2 : 1));
   }
   b.tap("dp_pooled", dp_pooled);
   // ---- a16/a17 head
@@ -455,28 +483,35 @@ int build_plan(dpb200_session* s) {
     T4 cat = b.act(Rd, P, P, 1280);
     T4 tmp = b.act(Rd, P, P, 512);
     T4 tmp256 = tmp; tmp256.C = 256;
-    auto gn = [&](const std::string& name, const T4& x, bf16* y, int ycs, int hw_in, int hw_out) {
+    // y: destination tensor, yoff: channel offset inside it (the ASPP branches write slices of the 1280-channel concat)
+    auto gn = [&](const std::string& name, const T4& x, const T4& y, int yoff, int ycs, int hw_in, int hw_out) {
       const Weight* w = b.weight(name);
       if (!w) return;
       const float* g = (const float*)w->d0; const float* be = (const float*)w->d1;
-      const bf16* xp = (const bf16*)x.p; const int C = x.C; const int R_ = Rd;
-      b.op([=](cudaStream_t st) { return launch_groupnorm_relu(xp, g, be, y, R_, hw_in, C, ycs, hw_out, nv, st); }, "groupnorm_relu",
-           (double)R_ * hw_in * C * 2 * 2 + (double)R_ * hw_out * C * 2);
+      const bf16* xp = (const bf16*)x.p; const bf16* xp2 = (const bf16*)x.p2; const int C = x.C; const int R_ = Rd;
+      bf16* yp = (bf16*)y.p + yoff; bf16* yp2 = y.p2 ? (bf16*)y.p2 + yoff : nullptr;
+      b.op([=](cudaStream_t st) {
+        if (strict) return launch_groupnorm_relu_split(xp, xp2, g, be, yp, yp2, R_, hw_in, C, ycs, hw_out, nv, st);
+        return launch_groupnorm_relu(xp, g, be, yp, R_, hw_in, C, ycs, hw_out, nv, st);
+      }, "groupnorm_relu", ((double)R_ * hw_in * C * 2 * 2 + (double)R_ * hw_out * C * 2) * (strict ? 2 : 1));
     };
     // ASPP branches (deeplab.py:112-144); branch 3 (rate 56 >= P) only ever sees its centre tap
     const int dil[3] = {1, 6, 12};
     for (int i = 0; i < 3; ++i) {
       Builder::ConvOpt o; o.k = i == 0 ? 1 : 3; o.dil = dil[i]; o.pad = i == 0 ? 0 : dil[i]; o.n_valid = nv; o.no_bias = true;
       b.conv(hp + "ASPP.convs." + std::to_string(i) + ".0", dp_pooled, tmp256, o);
-      gn(hp + "ASPP.convs." + std::to_string(i) + ".1", tmp256, (bf16*)cat.p + 256 * i, 1280, HW, HW);
+      gn(hp + "ASPP.convs." + std::to_string(i) + ".1", tmp256, cat, 256 * i, 1280, HW, HW);
     }
     { Builder::ConvOpt o; o.k = 1; o.n_valid = nv; o.no_bias = true;
       b.conv(hp + "ASPP.convs.3.0", dp_pooled, tmp256, o);
-      gn(hp + "ASPP.convs.3.1", tmp256, (bf16*)cat.p + 768, 1280, HW, HW); }
+      gn(hp + "ASPP.convs.3.1", tmp256, cat, 768, 1280, HW, HW); }
     T4 pooled = b.act(Rd, 1, 1, 256), pooled_c = b.act(Rd, 1, 1, 256);
-    b.op([=](cudaStream_t st) { return launch_avgpool((const bf16*)dp_pooled.p, (bf16*)pooled.p, Rd, HW, 256, nv, st); }, "avgpool");
+    b.op([=](cudaStream_t st) {
+      if (strict) return launch_avgpool_split((const bf16*)dp_pooled.p, (const bf16*)dp_pooled.p2, (bf16*)pooled.p, (bf16*)pooled.p2, Rd, HW, 256, nv, st);
+      return launch_avgpool((const bf16*)dp_pooled.p, (bf16*)pooled.p, Rd, HW, 256, nv, st);
+    }, "avgpool");
     { Builder::ConvOpt o; o.k = 1; o.n_valid = nv; o.no_bias = true; b.conv(hp + "ASPP.convs.4.1", pooled, pooled_c, o); }
-    gn(hp + "ASPP.convs.4.2", pooled_c, (bf16*)cat.p + 1024, 1280, 1, HW);
+    gn(hp + "ASPP.convs.4.2", pooled_c, cat, 1024, 1280, 1, HW);
     T4 proj = b.act(Rd, P, P, 256);
     { Builder::ConvOpt o; o.k = 1; o.relu = 1; o.n_valid = nv; o.no_bias = true; b.conv(hp + "ASPP.project.0", cat, proj, o); }
     T4 x = proj;
@@ -484,7 +519,7 @@ int build_plan(dpb200_session* s) {
       const std::string name = hp + "body_conv_fcn" + std::to_string(i + 1);
       Builder::ConvOpt o; o.k = 3; o.pad = 1; o.n_valid = nv; o.no_bias = true;
       b.conv(name, x, tmp, o);
-      gn(name + ".norm", tmp, (bf16*)hb[i & 1].p, 512, HW, HW);
+      gn(name + ".norm", tmp, hb[i & 1], 0, 512, HW, HW);
       x = hb[i & 1];
     }
     head_out = x;

@@ -117,6 +117,19 @@ int launch_predictor_upsample(const float* low, int R, int S, int Cpad, int Kc, 
 // Opt-in shared-memory attributes of the stage kernels on the current device (idempotent).
 int stage_kernels_init();
 
+// ---- strict (fp32-class) numerics: the same stage ops on bf16 hi/lo pairs (strict.cu) ---------------------------------
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi); every kernel reads both halves, computes in fp32 and splits again.
+struct RoiAlignSplit { const bf16* feat_lo[4]; void* out_lo; };
+int launch_maxpool3x3s2_split(const bf16* xh, const bf16* xl, bf16* yh, bf16* yl, int B, int H, int W, int C, cudaStream_t s);
+int launch_upsample2x_split(const bf16* xh, const bf16* xl, bf16* yh, bf16* yl, int B, int H, int W, int C, cudaStream_t s);
+// every argument is a {hi, lo} pointer pair
+int launch_decoder_merge_split(const bf16* const* a, const bf16* const* b3, const bf16* const* b4, const bf16* const* b5,
+                               bf16* const* out, int B, int H, int W, int C, cudaStream_t s);
+int launch_roi_align_split(const RoiAlignArgs& a, const RoiAlignSplit& sp, cudaStream_t s);
+int launch_groupnorm_relu_split(const bf16* xh, const bf16* xl, const float* gamma, const float* beta, bf16* yh, bf16* yl,
+                                int R, int HW, int C, int y_cstride, int out_hw, const int* n_valid, cudaStream_t s);
+int launch_avgpool_split(const bf16* xh, const bf16* xl, bf16* yh, bf16* yl, int R, int HW, int C, const int* n_valid, cudaStream_t s);
+
 // ---- per-box DensePose resample (visualizer.py:10-56) -------------------------------------------
 struct ResampleArgs {
   const float* coarse; const float* fine; const float* u; const float* v;   // [D, C, S, S] fp32

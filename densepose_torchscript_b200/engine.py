@@ -150,7 +150,10 @@ class Engine:
     def __init__(self, spec: ModelSpec, state_dict: Optional[Dict[str, torch.Tensor]] = None,
                  packed: Optional[Dict[str, Packed]] = None, device: Optional[torch.device] = None,
                  use_graph: bool = True, max_sessions: int = 4, strict: bool = False):
-        """max_sessions: how many plain (slot 0) sessions of distinct shapes stay cached; each owns a workspace
+        """strict: fp32-class numerics end to end (activations and weights as bf16 hi/lo pairs, three tensor-core passes
+        per product, fp32 accumulate; `packed` weights must then come from pack_state_dict(..., strict=True)) — the mode
+        in which proposals, NMS keep lists, detection counts and label maps are compared with the reference by index.
+        max_sessions: how many plain (slot 0) sessions of distinct shapes stay cached; each owns a workspace
         (0.9 GB at batch 1, 7.1 GB at batch 8 for R50-s1x), so a stream of differently sized images must not
         accumulate them. The least recently used one is dropped; HostPipeline slots are released by close()."""
         _lib.require_device()
@@ -162,7 +165,7 @@ class Engine:
         if packed is None:
             if state_dict is None:
                 raise ValueError("Engine needs a state_dict or packed weights")
-            packed = pack_state_dict(state_dict, spec, self.device)
+            packed = pack_state_dict(state_dict, spec, self.device, strict=strict)
         self.packed = packed
         cfg = _lib.ModelConfig()
         cfg.depth = spec.depth; cfg.head = 0 if spec.head == "v1convx" else 1
@@ -173,6 +176,7 @@ class Engine:
         for i in range(3):
             cfg.pixel_mean[i] = spec.pixel_mean[i]; cfg.pixel_std[i] = spec.pixel_std[i]
         cfg.input_rgb = int(spec.input_format == "RGB")
+        cfg.strict = int(strict)
         arr = (_lib.Weight * len(packed))()
         self._names = []
         for i, (name, (d0, d1, cin_pad, cout_pad)) in enumerate(packed.items()):

@@ -25,16 +25,26 @@ def round_up(v: int, m: int) -> int:
     return (v + m - 1) // m * m
 
 
-def pack_conv_weight(w: torch.Tensor, bias: Optional[torch.Tensor] = None):
-    """OIHW fp32 conv weight (or [out,in] linear weight) -> K-major bf16 [cout_pad, kh*kw*cin_pad].
-    Returns (packed, bias_fp32[cout_pad], cin_pad, cout_pad)."""
+def split_bf16(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 -> the strict mode's bf16 pair (hi, lo): hi = bf16(x), lo = bf16(x - hi); hi + lo carries 16 mantissa bits."""
+    hi = x.float().to(torch.bfloat16)
+    return hi, (x.float() - hi.float()).to(torch.bfloat16)
+
+
+def pack_conv_weight(w: torch.Tensor, bias: Optional[torch.Tensor] = None, strict: bool = False):
+    """OIHW fp32 conv weight (or [out,in] linear weight) -> K-major bf16 [cout_pad, kh*kw*cin_pad] (strict: three K
+    segments [w_hi | w_lo | w_hi] per tap). Returns (packed, bias_fp32[cout_pad], cin_pad, cout_pad)."""
     if w.dim() == 2:
         w = w[:, :, None, None]
     co, ci, kh, kw = w.shape
     cin_pad, cout_pad = round_up(ci, 64), round_up(co, 16)
     p = torch.zeros(cout_pad, kh, kw, cin_pad, dtype=torch.float32, device=w.device)
     p[:co, :, :, :ci] = w.detach().float().permute(0, 2, 3, 1)
-    packed = p.reshape(cout_pad, kh * kw * cin_pad).to(torch.bfloat16).contiguous()
+    if strict:
+        hi, lo = split_bf16(p)
+        packed = torch.stack([hi, lo, hi], dim=3).reshape(cout_pad, kh * kw * 3 * cin_pad).contiguous()
+    else:
+        packed = p.reshape(cout_pad, kh * kw * cin_pad).to(torch.bfloat16).contiguous()
     b = torch.zeros(cout_pad, dtype=torch.float32, device=w.device)
     if bias is not None:
         b[:co] = bias.detach().float()
@@ -46,14 +56,19 @@ def conv2d(x: torch.Tensor, packed: torch.Tensor, bias: Optional[torch.Tensor], 
            res: Optional[torch.Tensor] = None, res_shift: int = 0, out_fp32: bool = False,
            n_valid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
            block_n: int = 0, stages: int = 0, tiled: bool = False, epilogue: int = 0,
-           planar: bool = False, ks: int = 0, phase_taps: bool = False, pair: int = 0) -> torch.Tensor:
+           planar: bool = False, ks: int = 0, phase_taps: bool = False, pair: int = 0,
+           x_lo: Optional[torch.Tensor] = None, res_lo: Optional[torch.Tensor] = None,
+           out_lo: Optional[torch.Tensor] = None):
     """x: bf16 NHWC [N,H,W,Cin] (contiguous). Returns NHWC [N,Ho,Wo,cout_pad] bf16 (or fp32); with
-    planar=True the fp32 result is channel-planar [N,cout_pad,Ho,Wo]."""
+    planar=True the fp32 result is channel-planar [N,cout_pad,Ho,Wo].
+    Strict mode (x_lo given): x / res are bf16 (hi, lo) pairs, `packed` comes from pack_conv_weight(strict=True); a bf16
+    result is returned as the pair (hi, lo)."""
     _lib.require_device()
     assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
     n, h, w, cin = x.shape
     cout_pad, ktot = packed.shape
-    cin_pad = ktot // (kh * kw)
+    strict = x_lo is not None
+    cin_pad = ktot // (kh * kw * (3 if strict else 1))
     ho = (h + 2 * pad - dil * (kh - 1) - 1) // stride + 1
     wo = (w + 2 * pad - dil * (kw - 1) - 1) // stride + 1
     if phase_taps:          # ConvTranspose2d(k4,s2,p1) phases: one low-res output pixel per input pixel
@@ -84,8 +99,17 @@ def conv2d(x: torch.Tensor, packed: torch.Tensor, bias: Optional[torch.Tensor], 
     a.block_n, a.stages, a.tiled, a.ks = block_n, stages, int(tiled), ks
     a.phase_taps = int(phase_taps)
     a.pair = pair
+    if strict:
+        assert x_lo.dtype == torch.bfloat16 and x_lo.shape == x.shape and x_lo.is_contiguous()
+        a.x_lo = x_lo.data_ptr()
+        if res is not None:
+            assert res_lo is not None and res_lo.shape == res.shape and res_lo.is_contiguous()
+            a.res_lo = res_lo.data_ptr()
+        if out.dtype == torch.bfloat16:
+            out_lo = torch.empty_like(out) if out_lo is None else out_lo
+            a.y_lo = out_lo.data_ptr()
     check(lib.dpb200_conv2d(C.byref(a), _stream()), "dpb200_conv2d")
-    return out
+    return (out, out_lo) if (strict and out.dtype == torch.bfloat16) else out
 
 
 def preprocess(images: torch.Tensor, k: float, mean: Sequence[float], std: Sequence[float],

@@ -69,13 +69,20 @@ def _fold(sd, prefix) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     return w, (b.detach().float() if b is not None else None)
 
 
-def _pack_khwc(w_khwc: torch.Tensor, bias: Optional[torch.Tensor], device) -> Packed:
-    """w_khwc: [cout, kh, kw, cin] fp32."""
+def _pack_khwc(w_khwc: torch.Tensor, bias: Optional[torch.Tensor], device, strict: bool = False) -> Packed:
+    """w_khwc: [cout, kh, kw, cin] fp32. strict: every tap carries three K segments [w_hi | w_lo | w_hi] with
+    w_hi = bf16(w), w_lo = bf16(w - w_hi); the conv kernel pairs them with the activation halves (x_hi, x_hi, x_lo), so
+    the fp32 accumulator receives x_hi*w_hi + x_hi*w_lo + x_lo*w_hi (conv_igemm.cuh, strict mode)."""
     co, kh, kw, ci = w_khwc.shape
     cin_pad, cout_pad = round_up(ci, 64), round_up(co, 16)
     p = torch.zeros(cout_pad, kh, kw, cin_pad, dtype=torch.float32)
     p[:co, :, :, :ci] = w_khwc
-    packed = p.reshape(cout_pad, kh * kw * cin_pad).to(torch.bfloat16).contiguous().to(device)
+    if strict:
+        hi = p.to(torch.bfloat16)
+        lo = (p - hi.float()).to(torch.bfloat16)
+        packed = torch.stack([hi, lo, hi], dim=3).reshape(cout_pad, kh * kw * 3 * cin_pad).contiguous().to(device)
+    else:
+        packed = p.reshape(cout_pad, kh * kw * cin_pad).to(torch.bfloat16).contiguous().to(device)
     b = None
     if bias is not None:
         b = torch.zeros(cout_pad, dtype=torch.float32)
@@ -84,15 +91,15 @@ def _pack_khwc(w_khwc: torch.Tensor, bias: Optional[torch.Tensor], device) -> Pa
     return packed, b, cin_pad, cout_pad
 
 
-def _pack_conv(w_oihw: torch.Tensor, bias, device) -> Packed:
-    if w_oihw.dim() == 2:
-        w_oihw = w_oihw[:, :, None, None]
-    return _pack_khwc(w_oihw.permute(0, 2, 3, 1), bias, device)
-
-
-def pack_state_dict(sd: Dict[str, torch.Tensor], spec: ModelSpec, device) -> Dict[str, Packed]:
+def pack_state_dict(sd: Dict[str, torch.Tensor], spec: ModelSpec, device, strict: bool = False) -> Dict[str, Packed]:
+    """strict: weights for the fp32-class numerics mode (three K segments per tap, see _pack_khwc)."""
     sd = {k: v.detach().cpu() for k, v in canonicalize(sd).items()}
     out: Dict[str, Packed] = {}
+
+    def _pack_conv(w_oihw: torch.Tensor, bias, device) -> Packed:
+        if w_oihw.dim() == 2:
+            w_oihw = w_oihw[:, :, None, None]
+        return _pack_khwc(w_oihw.permute(0, 2, 3, 1), bias, device, strict)
 
     def conv(prefix, with_bias=True):
         w, b = _fold(sd, prefix)
@@ -112,7 +119,7 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], spec: ModelSpec, device) -> Dic
                     kx = 2 * kxq + dx - 1
                     if 0 <= kx <= 6:
                         sw[:, kyq, kxq, dy, dx, :3] = w[:, :, ky, kx]
-    out["backbone.bottom_up.stem.conv1"] = _pack_khwc(sw.reshape(64, 4, 1, 64), b, device)
+    out["backbone.bottom_up.stem.conv1"] = _pack_khwc(sw.reshape(64, 4, 1, 64), b, device, strict)
     for si, nb in enumerate(spec.blocks):
         for bi in range(nb):
             p = f"backbone.bottom_up.res{si + 2}.{bi}"
@@ -167,7 +174,7 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], spec: ModelSpec, device) -> Dic
             kys = [3 - 2 * t for t in range(2)] if py == 0 else [2 - 2 * t for t in range(2)]
             kxs = [3 - 2 * t for t in range(2)] if px == 0 else [2 - 2 * t for t in range(2)]
             sub = wt[:, :, kys, :][:, :, :, kxs]                                 # [ci, co, ty, tx]
-            out[pp + f"phase{py * 2 + px}"] = _pack_khwc(sub.permute(1, 2, 3, 0), bt, device)
+            out[pp + f"phase{py * 2 + px}"] = _pack_khwc(sub.permute(1, 2, 3, 0), bt, device, strict)
     # the four phases stacked on Cout: one GEMM launch whose N blocks are the phases (conv_igemm phase_taps)
     ph = [out.pop(pp + f"phase{i}") for i in range(4)]
     out[pp + "phases"] = (torch.cat([q[0] for q in ph], 0).contiguous(), torch.cat([q[1] for q in ph], 0).contiguous(),

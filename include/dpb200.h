@@ -71,6 +71,11 @@ typedef struct dpb200_conv2d_args {
                                each CTA staging half of the weight tile. 0 automatic (long-K 256-wide tiles), 1 off,
                                2 on (needs tiled == 0 and an N tile that is a multiple of 16; works with both
                                epilogues; measured neutral for the N=80 deconv phases, so not chosen there) */
+  /* Strict (fp32-class) numerics, selected by x_lo != NULL: activations are pairs of bf16 tensors with x = hi + lo
+   * (hi = bf16(x), lo = bf16(x - hi)); wgt is then packed per tap as three K segments [w_hi | w_lo | w_hi]
+   * ([cout_pad][kh*kw*3*cin_pad]) and the kernel accumulates x_hi*w_hi + x_hi*w_lo + x_lo*w_hi in fp32 (three
+   * tcgen05.mma passes into one TMEM accumulator). x_lo / res_lo / y_lo share the strides of x / res / y. */
+  const void* x_lo; const void* res_lo; void* y_lo;
 } dpb200_conv2d_args;
 
 int dpb200_conv2d(const dpb200_conv2d_args* a, void* stream);
@@ -190,6 +195,10 @@ typedef struct dpb200_model_config {
   int32_t min_size, max_size;
   float pixel_mean[3], pixel_std[3];
   int32_t input_rgb;        /* INPUT.FORMAT == "RGB"                                              */
+  int32_t strict;           /* 1: fp32-class numerics end to end — activations and weights as bf16 hi/lo pairs, three
+                               tensor-core passes per product, fp32 accumulate (the weights handed to
+                               dpb200_model_create must then be packed with three K segments per tap); the mode in
+                               which proposals, NMS keep lists and label maps are compared with the reference BY INDEX */
 } dpb200_model_config;
 
 /* One packed parameter. conv / linear / deconv-phase: data0 = bf16 [cout_pad][k*cin_pad], data1 = fp32

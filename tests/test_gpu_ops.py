@@ -156,6 +156,61 @@ def test_deconv_four_phases_in_one_launch(ops, tiled):
     assert bool((out[4:] == -3.0).all())
 
 
+STRICT_CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad, dil, relu, res(0 none, 1 same, 2 up2), fp32 out
+    (2, 25, 42, 64, 64, 1, 1, 0, 1, True, 0, False),
+    (1, 50, 84, 256, 256, 3, 1, 1, 1, True, 0, False),
+    (2, 25, 42, 128, 512, 1, 1, 0, 1, True, 1, False),
+    (2, 50, 84, 256, 128, 1, 2, 0, 1, False, 0, False),
+    (1, 50, 84, 512, 256, 1, 1, 0, 1, False, 2, False),
+    (40, 1, 1, 12544, 1024, 1, 1, 0, 1, True, 0, False),      # FC1: K = 3 x 12544
+    (3, 28, 28, 512, 512, 3, 1, 1, 1, True, 0, False),        # head conv
+    (2, 50, 84, 256, 15, 1, 1, 0, 1, False, 0, True),         # RPN predictor: fp32 output
+    (3, 28, 28, 256, 256, 3, 1, 12, 12, False, 0, False),     # ASPP, dilation 12
+]
+
+
+@pytest.mark.parametrize("case", STRICT_CASES)
+def test_conv_strict_mode_is_fp32_class(ops, case):
+    """Strict numerics: fp32 operands as bf16 (hi, lo) pairs, x_hi*w_hi + x_hi*w_lo + x_lo*w_hi accumulated in fp32 by
+    three tcgen05.mma passes. Against F.conv2d in fp64 on the un-rounded fp32 operands the error must be that of 16-bit
+    operands (2^-16-class), ~100x below the bf16 path's, and the returned (hi, lo) pair must be the split of one fp32."""
+    N, H, W, Cin, Cout, k, stride, pad, dil, relu, res_mode, fp32_out = case
+    g = torch.Generator().manual_seed(sum(case[:9]))
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=pad, dilation=dil)
+    res = None
+    if res_mode == 1:
+        res = torch.randn(ref.shape, generator=g)
+        ref = ref + res.double()
+    elif res_mode == 2:
+        res = torch.randn(N, Cout, (ref.shape[2] + 1) // 2, (ref.shape[3] + 1) // 2, generator=g)
+        ref = ref + F.interpolate(res.double(), scale_factor=2.0, mode="nearest")[:, :, :ref.shape[2], :ref.shape[3]]
+    if relu:
+        ref = F.relu(ref)
+    to_nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().cuda()      # noqa: E731
+    xh, xl = ops.split_bf16(to_nhwc(x))
+    rh, rl = ops.split_bf16(to_nhwc(res)) if res is not None else (None, None)
+    packed, bias, _, cout_pad = ops.pack_conv_weight(w.cuda(), b.cuda(), strict=True)
+    out = ops.conv2d(xh, packed, bias, k, k, stride=stride, pad=pad, dil=dil, relu=relu, res=rh, res_lo=rl,
+                     res_shift=1 if res_mode == 2 else 0, x_lo=xl, out_fp32=fp32_out)
+    torch.cuda.synchronize()
+    if fp32_out:
+        got = nchw(out[..., :Cout]).double()
+    else:
+        hi, lo = out
+        val = hi.float() + lo.float()
+        h2, l2 = ops.split_bf16(val)
+        assert torch.equal(h2, hi) and torch.equal(l2, lo)              # a canonical split of one fp32 value
+        got = nchw(val[..., :Cout]).double()
+    err = float((got - ref).abs().max())
+    scale = float(ref.abs().max())
+    assert err <= scale * 2.0 ** -13, (err, scale)                      # bf16 path: ~2^-8 of the largest magnitude
+    assert float((got - ref).norm() / ref.norm()) < 2e-5                # bf16 path: ~3e-3
+
+
 def test_conv_fp32_out_and_n_valid(ops):
     g = torch.Generator().manual_seed(5)
     x = bf16(torch.randn(9, 256, 28, 28, generator=g))
