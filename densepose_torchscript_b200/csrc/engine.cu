@@ -229,9 +229,10 @@ int build_plan(dpb200_session* s) {
     p.dst_lo = reinterpret_cast<bf16*>(x0.p2);
     p.variant = 0; p.tables = nullptr;
     dpb200_session* ss = s;
+    // (allocated for every session so that dpb200_session_workspace_bytes does not depend on the input type)
+    int2* tab = (int2*)b.alloc((size_t)(1 + s->Hr + s->Wr) * sizeof(int2));
     if (s->src_u8) {
       // uint8 frames (run.py:33-36): ATen's fixed-point weights, rebuilt on the device every run (two small CTAs)
-      int2* tab = (int2*)b.alloc((size_t)(1 + s->Hr + s->Wr) * sizeof(int2));
       p.tables = tab;
       const double scale = 1.0 / s->k;
       const int H0 = s->H0, W0 = s->W0, Hr = s->Hr, Wr = s->Wr;
