@@ -92,7 +92,7 @@ class ModelConfig(C.Structure):
         ("score_thresh", f32), ("nms_test", f32), ("rpn_nms", f32),
         ("dets_per_image", i32), ("rpn_pre_topk", i32), ("rpn_post_topk", i32),
         ("min_size", i32), ("max_size", i32),
-        ("pixel_mean", f32 * 3), ("pixel_std", f32 * 3), ("input_rgb", i32), ("strict", i32),
+        ("pixel_mean", f32 * 3), ("pixel_std", f32 * 3), ("input_rgb", i32), ("extra_ch", i32 * 5), ("strict", i32),
     ]
 
 
@@ -103,7 +103,7 @@ class Weight(C.Structure):
 class ForwardIO(C.Structure):
     _fields_ = [
         ("images", vp), ("bgr", i32), ("pred_boxes", vp), ("scores", vp), ("det_count", vp), ("det_offsets", vp),
-        ("coarse", vp), ("fine", vp), ("u", vp), ("v", vp), ("out_half", i32),
+        ("coarse", vp), ("fine", vp), ("u", vp), ("v", vp), ("out_half", i32), ("extra", vp * 5),
     ]
 
 
@@ -129,7 +129,7 @@ _proto("dpb200_roi_align", C.c_int, [C.POINTER(RoiAlignArgs), vp])
 _proto("dpb200_box_predict", C.c_int, [C.POINTER(BoxPredictArgs), vp])
 _proto("dpb200_groupnorm_relu", C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp])
 _proto("dpb200_avgpool", C.c_int, [vp, vp, i32, i32, i32, vp, vp])
-_proto("dpb200_predictor_upsample", C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp])
+_proto("dpb200_predictor_upsample", C.c_int, [vp, i32, i32, i32, vp, C.POINTER(vp), C.POINTER(i32), i32, vp])
 _proto("dpb200_dp_resample", C.c_int, [C.POINTER(ResampleArgs), vp])
 _proto("dpb200_model_create", C.c_int, [C.POINTER(ModelConfig), C.POINTER(Weight), i32, C.POINTER(vp)])
 _proto("dpb200_model_destroy", None, [vp])

@@ -43,9 +43,26 @@ class ModelSpec:
     def out_size(self) -> int:
         return 4 * self.pooler_res
 
+    @property
+    def extra_heads(self) -> Tuple[Tuple[str, int], ...]:
+        """Confidence heads the predictor carries beside coarse / fine / u / v, in the engine's channel order
+        (chart_with_confidence.py:50-89): (name, channels)."""
+        heads = []
+        if self.uv_confidence:
+            heads.append(("sigma_2", 25))
+            if self.uv_confidence == "indep_aniso":
+                heads += [("kappa_u", 25), ("kappa_v", 25)]
+        if self.segm_confidence:
+            heads += [("fine_segm_confidence", 1), ("coarse_segm_confidence", 1)]
+        return tuple(heads)
 
-def _mk(name, depth, head, decoder, res, coarse) -> ModelSpec:
-    return ModelSpec(name=name, depth=depth, head=head, decoder_on=decoder, pooler_res=res, coarse_ch=coarse)
+
+EXTRA_HEAD_ORDER = ("sigma_2", "kappa_u", "kappa_v", "fine_segm_confidence", "coarse_segm_confidence")
+
+
+def _mk(name, depth, head, decoder, res, coarse, uv="", segm=False) -> ModelSpec:
+    return ModelSpec(name=name, depth=depth, head=head, decoder_on=decoder, pooler_res=res, coarse_ch=coarse,
+                     uv_confidence=uv, segm_confidence=segm)
 
 
 BUILTIN: Dict[str, ModelSpec] = {s.name: s for s in [
@@ -55,6 +72,9 @@ BUILTIN: Dict[str, ModelSpec] = {s.name: s for s in [
     _mk("densepose_rcnn_R_101_FPN_s1x", 101, "v1convx", True, 28, 2),
     _mk("densepose_rcnn_R_50_FPN_DL_s1x", 50, "deeplab", True, 28, 2),
     _mk("densepose_rcnn_R_101_FPN_DL_s1x", 101, "deeplab", True, 28, 2),
+    # two of the confidence ("WC") variants (README.md:208-330 of the reference): same path, extra predictor heads
+    _mk("densepose_rcnn_R_50_FPN_WC1_s1x", 50, "v1convx", True, 28, 2, "iid_iso", False),
+    _mk("densepose_rcnn_R_50_FPN_WC2M_s1x", 50, "v1convx", True, 28, 2, "indep_aniso", True),
 ]}
 
 

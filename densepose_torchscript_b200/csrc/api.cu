@@ -139,10 +139,13 @@ int dpb200_groupnorm_relu(const void* x, const float* gamma, const float* beta, 
 int dpb200_avgpool(const void* x, void* y, int32_t r, int32_t hw, int32_t c, const int32_t* n_valid, void* stream) {
   return launch_avgpool((const bf16*)x, (bf16*)y, r, hw, c, n_valid, S(stream));
 }
-int dpb200_predictor_upsample(const float* low, int32_t r, int32_t s, int32_t cpad, int32_t kc,
-                              const int32_t* n_valid, float* coarse, float* fine, float* u, float* v,
-                              int32_t planar, void* stream) {
-  return launch_predictor_upsample(low, r, s, cpad, kc, n_valid, coarse, fine, u, v, planar, 0, S(stream));
+int dpb200_predictor_upsample(const float* low, int32_t r, int32_t s, int32_t cpad, const int32_t* n_valid,
+                              void* const* out, const int32_t* ch, int32_t n, void* stream) {
+  if (!out || !ch || n < 1 || n > kMaxUpsampleOutputs) { set_error("predictor_upsample: bad output list"); return -1; }
+  UpsampleOutputs o{};
+  o.n = n;
+  for (int i = 0; i < n; ++i) { o.dst[i] = out[i]; o.ch[i] = ch[i]; o.total += ch[i]; }
+  return launch_predictor_upsample(low, r, s, cpad, n_valid, o, 0, S(stream));
 }
 
 int dpb200_dp_resample(const dpb200_resample_args* a, void* stream) {

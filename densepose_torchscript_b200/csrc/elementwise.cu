@@ -616,25 +616,32 @@ __device__ __forceinline__ float lerp_cl(bool vec, float w00, float p00, float w
 
 template <typename OutT, bool kSmall>
 __global__ void __launch_bounds__(256)
-predictor_upsample_planar_kernel(const float* __restrict__ low, int S, int Cpad, int Kc,
-                                 const int* __restrict__ n_valid, OutT* __restrict__ coarse,
-                                 OutT* __restrict__ fine, OutT* __restrict__ u, OutT* __restrict__ v) {
+predictor_upsample_planar_kernel(const float* __restrict__ low, int S, int Cpad, const int* __restrict__ n_valid,
+                                 const UpsampleOutputs outs) {
   const int r = blockIdx.y;
   if (n_valid != nullptr && r >= *n_valid) return;
   const int Sh = S >> 1, So = 2 * S;
   const int G = S >> 1;                        // 4-column output strips per row
-  const int C = Kc + 75;
+  const int C = outs.total;
   const int KB = (S + 1 + kUpRows - 1) / kUpRows;
   const int item = blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= KB * C * G) return;
   const int g = item % G;
   const int c = (item / G) % C;
   const int kb = item / (G * C);
-  OutT* dst; int cc, nc;
-  if (c < Kc) { dst = coarse; cc = c; nc = Kc; }
-  else if (c < Kc + 25) { dst = fine; cc = c - Kc; nc = 25; }
-  else if (c < Kc + 50) { dst = u; cc = c - Kc - 25; nc = 25; }
-  else { dst = v; cc = c - Kc - 50; nc = 25; }
+  // channel c of the fused deconv output belongs to output tensor `seg` (coarse, fine, u, v, then the confidence heads)
+  int seg = 0, c0 = 0;
+  bool found = false;
+#pragma unroll
+  for (int i = 0; i < kMaxUpsampleOutputs; ++i) {
+    if (!found && i < outs.n) {
+      if (c < c0 + outs.ch[i]) { seg = i; found = true; }
+      else c0 += outs.ch[i];
+    }
+  }
+  OutT* dst = reinterpret_cast<OutT*>(outs.dst[seg]);
+  const int cc = c - c0, nc = outs.ch[seg];
+  if (dst == nullptr) return;                  // a head the caller does not want
   const bool vec = cc < nc - (nc & 7);
   OutT* plane = dst + ((long long)r * nc + cc) * So * So + 4 * g;
   const long long plane_sz = (long long)Sh * Sh;
@@ -689,17 +696,20 @@ predictor_upsample_planar_kernel(const float* __restrict__ low, int S, int Cpad,
 
 int stage_kernels_init() { return 0; }
 
-int launch_predictor_upsample(const float* low, int R, int S, int Cpad, int Kc, const int* n_valid,
-                              void* coarse, void* fine, void* u, void* v, int planar, int out_half,
-                              cudaStream_t s) {
-  if (!planar) { set_error("predictor_upsample: only the phase-planar layout [R,2,2,Cpad,S/2,S/2] is supported"); return -1; }
-  if (S % 2 || Kc + 75 > Cpad) { set_error("predictor_upsample: bad shape S %d Cpad %d", S, Cpad); return -1; }
+int launch_predictor_upsample(const float* low, int R, int S, int Cpad, const int* n_valid, const UpsampleOutputs& outs,
+                              int out_half, cudaStream_t s) {
+  int total = 0;
+  for (int i = 0; i < outs.n; ++i) total += outs.ch[i];
+  if (S % 2 || outs.n < 1 || outs.n > kMaxUpsampleOutputs || total != outs.total || total > Cpad) {
+    set_error("predictor_upsample: bad shape S %d Cpad %d channels %d", S, Cpad, total);
+    return -1;
+  }
   if (R == 0) return 0;
   const int KB = (S + 1 + kUpRows - 1) / kUpRows;
-  const int items = KB * (Kc + 75) * (S / 2);
+  const int items = KB * total * (S / 2);
   dim3 grid((items + 255) / 256, R);
   const bool small = 4 * S <= 128;      // ATen switches kernels on output h + w = 2S + 2S
-#define DPB_UP(T, SM) predictor_upsample_planar_kernel<T, SM><<<grid, 256, 0, s>>>(low, S, Cpad, Kc, n_valid, (T*)coarse, (T*)fine, (T*)u, (T*)v)
+#define DPB_UP(T, SM) predictor_upsample_planar_kernel<T, SM><<<grid, 256, 0, s>>>(low, S, Cpad, n_valid, outs)
   if (out_half) { if (small) DPB_UP(__half, true); else DPB_UP(__half, false); }
   else { if (small) DPB_UP(float, true); else DPB_UP(float, false); }
 #undef DPB_UP

@@ -530,7 +530,9 @@ int build_plan(dpb200_session* s) {
   // Output pixel (2y+py, 2x+px) of the deconv only depends on phase (py,px): the phase GEMMs (the four N blocks
   // of one launch) each write their own channel-planar fp32 block low[r][py][px][c][P][P] (TMEM lane = pixel,
   // so planar stores coalesce).
-  const int Cp = round_up(cfg.coarse_ch + 75, 16);
+  int extra_total = 0;
+  for (int i = 0; i < 5; ++i) extra_total += cfg.extra_ch[i];
+  const int Cp = round_up(cfg.coarse_ch + 75 + extra_total, 16);
   const int S2 = 2 * P;
   T4 low = b.act(Rd, 4 * Cp, P, P, 1);      // [Rd][2][2][Cp][P][P]
   s->low = (float*)low.p; s->low_S = S2; s->low_C = Cp;
@@ -545,10 +547,19 @@ int build_plan(dpb200_session* s) {
   {
     dpb200_session* ss = s;
     const int Kc = cfg.coarse_ch;
-    b.op([ss, Rd, Kc, nv](cudaStream_t st) {
-      return launch_predictor_upsample(ss->low, Rd, ss->low_S, ss->low_C, Kc, nv, ss->io->coarse, ss->io->fine,
-                                       ss->io->u, ss->io->v, 1, ss->io->out_half, st);
-    }, "predictor_upsample", (double)low.elems() * 4 + (double)Rd * (cfg.coarse_ch + 75) * (4.0 * P) * (4.0 * P) * 4);
+    int extra_ch[5];
+    for (int i = 0; i < 5; ++i) extra_ch[i] = cfg.extra_ch[i];
+    b.op([ss, Rd, Kc, nv, extra_ch](cudaStream_t st) {
+      UpsampleOutputs o{};
+      void* base[4] = {ss->io->coarse, ss->io->fine, ss->io->u, ss->io->v};
+      const int ch[4] = {Kc, 25, 25, 25};
+      for (int i = 0; i < 4; ++i) { o.dst[o.n] = base[i]; o.ch[o.n] = ch[i]; o.total += ch[i]; ++o.n; }
+      for (int i = 0; i < 5; ++i) {
+        if (extra_ch[i] == 0) continue;
+        o.dst[o.n] = ss->io->extra[i]; o.ch[o.n] = extra_ch[i]; o.total += extra_ch[i]; ++o.n;
+      }
+      return launch_predictor_upsample(ss->low, Rd, ss->low_S, ss->low_C, nv, o, ss->io->out_half, st);
+    }, "predictor_upsample", (double)low.elems() * 4 + (double)Rd * (cfg.coarse_ch + 75 + extra_total) * (4.0 * P) * (4.0 * P) * 4);
   }
   return b.fail;
 }
@@ -560,6 +571,10 @@ extern "C" {
 int dpb200_model_create(const dpb200_model_config* cfg, const dpb200_weight* w, int32_t n, dpb200_model** out) {
   if (!cfg || !w || !out) { set_error("model_create: null argument"); return -1; }
   if (cfg->depth != 50 && cfg->depth != 101) { set_error("model_create: depth %d unsupported", cfg->depth); return -1; }
+  for (int i = 0; i < 5; ++i) {
+    const int want = i < 3 ? 25 : 1;
+    if (cfg->extra_ch[i] != 0 && cfg->extra_ch[i] != want) { set_error("model_create: extra_ch[%d] must be 0 or %d", i, want); return -1; }
+  }
   if (cfg->rpn_pre_topk > 1024 || cfg->rpn_post_topk > 1024 || cfg->dets_per_image > 1024) {
     set_error("model_create: top-k limits above 1024 unsupported"); return -1;
   }
@@ -599,7 +614,9 @@ void dpb200_session_destroy(dpb200_session* s) { delete s; }
 static bool same_io(const dpb200_forward_io& a, const dpb200_forward_io& b) {
   return a.images == b.images && a.bgr == b.bgr && a.pred_boxes == b.pred_boxes && a.scores == b.scores &&
          a.det_count == b.det_count && a.det_offsets == b.det_offsets && a.coarse == b.coarse &&
-         a.fine == b.fine && a.u == b.u && a.v == b.v && a.out_half == b.out_half;
+         a.fine == b.fine && a.u == b.u && a.v == b.v && a.out_half == b.out_half &&
+         a.extra[0] == b.extra[0] && a.extra[1] == b.extra[1] && a.extra[2] == b.extra[2] && a.extra[3] == b.extra[3] &&
+         a.extra[4] == b.extra[4];
 }
 
 static int run_ops(dpb200_session* s, cudaStream_t st) {

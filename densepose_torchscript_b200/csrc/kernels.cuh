@@ -107,12 +107,15 @@ int launch_groupnorm_relu(const bf16* x, const float* gamma, const float* beta, 
 // mean over HW: [R, HW, C] -> [R, C]  (AdaptiveAvgPool2d(1), deeplab.py:99)
 int launch_avgpool(const bf16* x, bf16* y, int R, int HW, int C, const int* n_valid, cudaStream_t s);
 
-// ---- predictor tail: bilinear x2 of the deconv output, NHWC fp32 -> four NCHW fp32 tensors -------
-// low: [R, S, S, Cpad] fp32 (channels: coarse[Kc], fine[25], u[25], v[25]); outputs [R, C, 2S, 2S].
-// planar != 0: low is [R, 2, 2, Cpad, S/2, S/2] (deconv output phases (py, px) as separate channel planes).
-int launch_predictor_upsample(const float* low, int R, int S, int Cpad, int Kc, const int* n_valid,
-                              void* coarse, void* fine, void* u, void* v, int planar, int out_half,
-                              cudaStream_t s);
+// ---- predictor tail: bilinear x2 of the deconv output (chart.py:62-90) -> NCHW fp32 / fp16 tensors ---------------------
+// low: [R, 2, 2, Cpad, S/2, S/2] fp32, the deconv output phases (py, px) as separate channel planes; channels run
+// coarse[Kc], fine[25], u[25], v[25] and then the confidence heads a WC* model carries (chart_with_confidence.py:50-89:
+// sigma_2[25], kappa_u[25], kappa_v[25], fine_segm_confidence[1], coarse_segm_confidence[1]). Output i is [R, ch[i], 2S, 2S];
+// a null dst skips that head.
+static constexpr int kMaxUpsampleOutputs = 9;
+struct UpsampleOutputs { void* dst[kMaxUpsampleOutputs]; int ch[kMaxUpsampleOutputs]; int n; int total; };
+int launch_predictor_upsample(const float* low, int R, int S, int Cpad, const int* n_valid, const UpsampleOutputs& outs,
+                              int out_half, cudaStream_t s);
 
 // Opt-in shared-memory attributes of the stage kernels on the current device (idempotent).
 int stage_kernels_init();

@@ -6,7 +6,7 @@ import torch
 
 from . import _lib
 from ._lib import lib, check
-from .config import ModelSpec
+from .config import EXTRA_HEAD_ORDER, ModelSpec
 from .weights import Packed, pack_state_dict
 
 _DTYPES = {0: torch.bfloat16, 1: torch.float32, 2: torch.int32, 3: torch.uint8}
@@ -41,12 +41,16 @@ class Session:
         self.fine = torch.zeros(n, 25, s, s, device=dev, dtype=odt)
         self.u = torch.zeros(n, 25, s, s, device=dev, dtype=odt)
         self.v = torch.zeros(n, 25, s, s, device=dev, dtype=odt)
+        # confidence heads of a WC* model (sigma_2 / kappa_u / kappa_v / segm confidences): extra outputs (f4)
+        self.extra = {name: torch.zeros(n, ch, s, s, device=dev, dtype=odt) for name, ch in spec.extra_heads}
         self.io = _lib.ForwardIO()
         self.io.pred_boxes = self.pred_boxes.data_ptr(); self.io.scores = self.scores.data_ptr()
         self.io.det_count = self.det_count.data_ptr(); self.io.det_offsets = self.det_offsets.data_ptr()
         self.io.coarse = self.coarse.data_ptr(); self.io.fine = self.fine.data_ptr()
         self.io.u = self.u.data_ptr(); self.io.v = self.v.data_ptr()
         self.io.out_half = int(out_half)
+        for i, name in enumerate(EXTRA_HEAD_ORDER):
+            self.io.extra[i] = self.extra[name].data_ptr() if name in self.extra else None
         # launches go to a private stream (the legacy default stream cannot be graph-captured); run() orders
         # it after / before the caller's current stream with events, so the semantics stay "enqueued on the
         # current stream"
@@ -141,6 +145,8 @@ class Session:
                 "pred_densepose_u": own(self.u[o:o + d]),
                 "pred_densepose_v": own(self.v[o:o + d]),
             })
+            for name, t in self.extra.items():      # WC* models: the confidence heads the reference builds but never emits
+                out[-1]["pred_densepose_" + name] = own(t[o:o + d])
         return out
 
 
@@ -177,6 +183,9 @@ class Engine:
             cfg.pixel_mean[i] = spec.pixel_mean[i]; cfg.pixel_std[i] = spec.pixel_std[i]
         cfg.input_rgb = int(spec.input_format == "RGB")
         cfg.strict = int(strict)
+        heads = dict(spec.extra_heads)
+        for i, name in enumerate(EXTRA_HEAD_ORDER):
+            cfg.extra_ch[i] = heads.get(name, 0)
         arr = (_lib.Weight * len(packed))()
         self._names = []
         for i, (name, (d0, d1, cin_pad, cout_pad)) in enumerate(packed.items()):
@@ -278,11 +287,11 @@ class HostPipeline:
             # two rotating result sets for the big tensors (full capacity, pinned): the set handed to the caller by one
             # call is never the one the next call fills
             s0 = self.slots[0]["sess"]
-            self.big_dev_names = ("coarse", "fine", "u", "v")
+            self.big_dev_names = ("coarse", "fine", "u", "v") + tuple(n for n, _ in engine.spec.extra_heads)
             self.sets = []
             if not extract:
                 for _ in range(2):
-                    self.sets.append([torch.empty(getattr(s0, n).shape, dtype=getattr(s0, n).dtype).pin_memory()
+                    self.sets.append([torch.empty(self._big(s0, n).shape, dtype=self._big(s0, n).dtype).pin_memory()
                                       for n in self.big_dev_names])
         self._set = 0
         self.h2d_bytes = self.slots[0]["host_in"].numel() * self.slots[0]["host_in"].element_size()
@@ -291,6 +300,10 @@ class HostPipeline:
         # capacity figure (every row): what a count-unaware copy would move per step
         self.d2h_bytes = self.small_d2h_bytes + self.row_bytes * batch * engine.spec.dets_per_image
         self._next = 0
+
+    @staticmethod
+    def _big(sess, name):
+        return sess.extra[name] if name in sess.extra else getattr(sess, name)
 
     def close(self):
         """Drops the slots' sessions (workspaces, output and staging buffers) from the engine."""
@@ -318,18 +331,18 @@ class HostPipeline:
         if n:
             with torch.cuda.device(self.engine.device), torch.cuda.stream(sess.stream):
                 for hbuf, name in zip(host, self.big_dev_names):
-                    hbuf[:n].copy_(getattr(sess, name)[:n], non_blocking=True)
+                    hbuf[:n].copy_(self._big(sess, name)[:n], non_blocking=True)
             sess.stream.synchronize()
         self.last_d2h_bytes = self.small_d2h_bytes + n * self.row_bytes
-        coarse, fine, u, v = host
+        keys = ("coarse_segm", "fine_segm", "u", "v") + self.big_dev_names[4:]
         out = []
         for b in range(sess.batch):
             d, o = int(counts[b]), int(offs[b])
-            out.append({"image_size": torch.tensor([sess.h0, sess.w0], dtype=torch.int64),
-                        "pred_boxes": boxes[b, :d], "scores": scores[b, :d],
-                        "pred_classes": torch.zeros(d, dtype=torch.int64),
-                        "pred_densepose_coarse_segm": coarse[o:o + d], "pred_densepose_fine_segm": fine[o:o + d],
-                        "pred_densepose_u": u[o:o + d], "pred_densepose_v": v[o:o + d]})
+            res = {"image_size": torch.tensor([sess.h0, sess.w0], dtype=torch.int64),
+                   "pred_boxes": boxes[b, :d], "scores": scores[b, :d], "pred_classes": torch.zeros(d, dtype=torch.int64)}
+            for key, hbuf in zip(keys, host):
+                res["pred_densepose_" + key] = hbuf[o:o + d]
+            out.append(res)
         return out
 
     def _collect_extracted(self, sl, boxes, scores, counts) -> List[Dict[str, object]]:

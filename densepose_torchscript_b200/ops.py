@@ -271,16 +271,19 @@ def avgpool(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
-def predictor_upsample(low: torch.Tensor, kc: int):
+def predictor_upsample(low: torch.Tensor, channels: Sequence[int]):
     """low: the phase-planar fp32 [R,2,2,Cpad,S/2,S/2] the deconv GEMM writes (low-res pixel (2*yy+py, 2*xx+px) at
-    [r,py,px,c,yy,xx]) -> (coarse [R,kc,2S,2S], fine, u, v) NCHW fp32."""
+    [r,py,px,c,yy,xx]); `channels`: how its leading channels split into heads, e.g. (kc, 25, 25, 25) for coarse / fine /
+    u / v (+ the confidence heads of a WC* model). Returns one NCHW fp32 [R,ch,2S,2S] tensor per head."""
     r, _, _, cpad, sh, _ = low.shape
     s = 2 * sh
     dev = low.device
     assert low.is_contiguous() and low.dtype == torch.float32
-    outs = [torch.empty(r, c, 2 * s, 2 * s, device=dev) for c in (kc, 25, 25, 25)]
-    check(lib.dpb200_predictor_upsample(low.data_ptr(), r, s, cpad, kc, None, *[o.data_ptr() for o in outs],
-                                        1, _stream()), "dpb200_predictor_upsample")
+    outs = [torch.empty(r, c, 2 * s, 2 * s, device=dev) for c in channels]
+    ptrs = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+    ch = (C.c_int32 * len(outs))(*channels)
+    check(lib.dpb200_predictor_upsample(low.data_ptr(), r, s, cpad, None, ptrs, ch, len(outs), _stream()),
+          "dpb200_predictor_upsample")
     return outs
 
 

@@ -18,6 +18,8 @@ from .weights import pack_state_dict
 
 
 class DensePoseB200Predictor(nn.Module):
+    extra_names: List[str]          # (class-level annotation: TorchScript cannot infer the type of an empty list)
+
     def __init__(self, spec: ModelSpec, state_dict: Dict[str, torch.Tensor]):
         super().__init__()
         packed = pack_state_dict(state_dict, spec, "cpu")
@@ -32,11 +34,13 @@ class DensePoseB200Predictor(nn.Module):
         self.min_size: int = spec.min_size          # defaults.py:59-60
         self.max_size: int = spec.max_size
         self.input_format: str = spec.input_format  # defaults.py:62
+        # confidence heads of a WC* model (chart_with_confidence.py:50-89): extra output keys pred_densepose_<name>
+        self.extra_names = [name for name, _ in spec.extra_heads]
 
     def forward(self, original_image: torch.Tensor, bgr: bool = True) -> Dict[str, torch.Tensor]:
         out = torch.ops.dpb200.forward(original_image, bgr, self.weights, self.table, self.names, self.cfg_i,
                                        self.cfg_f, self.dtype_probe)
-        return {
+        res = {
             "image_size": out[0],
             "pred_boxes": out[1],
             "scores": out[2],
@@ -46,3 +50,6 @@ class DensePoseB200Predictor(nn.Module):
             "pred_densepose_u": out[6],
             "pred_densepose_v": out[7],
         }
+        for i in range(len(self.extra_names)):
+            res["pred_densepose_" + self.extra_names[i]] = out[8 + i]
+        return res

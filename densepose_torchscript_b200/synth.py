@@ -85,14 +85,19 @@ def layer_table(spec: ModelSpec) -> List[Tuple[str, str, Tuple[int, ...]]]:
     t.append((pp + "index_uv_lowres", "deconv", (512, 25, 4, 4)))
     t.append((pp + "u_lowres", "deconv", (512, 25, 4, 4)))
     t.append((pp + "v_lowres", "deconv", (512, 25, 4, 4)))
+    for head, ch in getattr(spec, "extra_heads", ()):          # WC* confidence heads (chart_with_confidence.py:50-89)
+        t.append((pp + head + "_lowres", "deconv", (512, ch, 4, 4)))
     return t
 
 
 def load_scales(spec: ModelSpec) -> Optional[Dict[str, float]]:
     if not os.path.exists(SCALES_PATH):
         return None
+    import re
     with open(SCALES_PATH) as f:
-        return json.load(f).get(spec.name)
+        allsc = json.load(f)
+    # the WC* variants share every calibrated layer with their base config (their extra heads keep scale 1)
+    return allsc.get(spec.name) or allsc.get(re.sub(r"_WC\d+M?", "", spec.name))
 
 
 def make_state_dict(spec: ModelSpec, seed: int = 0, scales: Optional[Dict[str, float]] = None,

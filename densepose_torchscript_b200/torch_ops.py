@@ -38,7 +38,8 @@ def release_engines() -> None:
 def spec_to_lists(spec: ModelSpec) -> Tuple[List[int], List[float]]:
     ci = [spec.depth, 0 if spec.head == "v1convx" else 1, int(spec.decoder_on), spec.pooler_res, spec.coarse_ch,
           spec.dets_per_image, spec.rpn_pre_topk, spec.rpn_post_topk, spec.min_size, spec.max_size,
-          int(spec.input_format == "RGB")]
+          int(spec.input_format == "RGB"), {"": 0, "iid_iso": 1, "indep_aniso": 2}[spec.uv_confidence],
+          int(spec.segm_confidence)]
     cf = [spec.score_thresh, spec.nms_test, spec.rpn_nms] + list(spec.pixel_mean) + list(spec.pixel_std)
     return ci, [float(x) for x in cf]
 
@@ -47,6 +48,8 @@ def lists_to_spec(ci: List[int], cf: List[float]) -> ModelSpec:
     return ModelSpec(name="exported", depth=ci[0], head="v1convx" if ci[1] == 0 else "deeplab", decoder_on=bool(ci[2]),
                      pooler_res=ci[3], coarse_ch=ci[4], dets_per_image=ci[5], rpn_pre_topk=ci[6], rpn_post_topk=ci[7],
                      min_size=ci[8], max_size=ci[9], input_format="RGB" if ci[10] else "BGR",
+                     uv_confidence=("", "iid_iso", "indep_aniso")[ci[11]] if len(ci) > 11 else "",
+                     segm_confidence=bool(ci[12]) if len(ci) > 12 else False,
                      score_thresh=cf[0], nms_test=cf[1], rpn_nms=cf[2], pixel_mean=tuple(cf[3:6]), pixel_std=tuple(cf[6:9]))
 
 
@@ -132,9 +135,12 @@ def _forward_cuda(image, bgr, blob, table, names, cfg_i, cfg_f, dtype_probe):
     dt = dtype_probe.dtype if dtype_probe.dtype in (torch.float16, torch.bfloat16) else torch.float32
     # a `.half()` module gets its DensePose tensors as fp16 straight from the kernel (no conversion pass)
     res = eng.forward_batch(image.unsqueeze(0), bgr, out_half=(dt == torch.float16), copy=False)[0]   # cloned below
-    return [res["image_size"], res["pred_boxes"].clone(), res["scores"].to(dt, copy=True), res["pred_classes"],
-            res["pred_densepose_coarse_segm"].to(dt, copy=True), res["pred_densepose_fine_segm"].to(dt, copy=True),
-            res["pred_densepose_u"].to(dt, copy=True), res["pred_densepose_v"].to(dt, copy=True)]
+    out = [res["image_size"], res["pred_boxes"].clone(), res["scores"].to(dt, copy=True), res["pred_classes"],
+           res["pred_densepose_coarse_segm"].to(dt, copy=True), res["pred_densepose_fine_segm"].to(dt, copy=True),
+           res["pred_densepose_u"].to(dt, copy=True), res["pred_densepose_v"].to(dt, copy=True)]
+    # WC* models: the confidence heads, in ModelSpec.extra_heads order (the scripted module names them)
+    out += [res["pred_densepose_" + name].to(dt, copy=True) for name, _ in eng.spec.extra_heads]
+    return out
 
 
 # The image may arrive on the CPU (run.py feeds torch.from_numpy frames): dispatch on every backend and

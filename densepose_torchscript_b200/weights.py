@@ -166,7 +166,9 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], spec: ModelSpec, device, strict
         for i in range(8):
             conv(hp + f"body_conv_fcn{i + 1}")
     pp = "roi_heads.densepose_predictor."
-    names = ("ann_index_lowres", "index_uv_lowres", "u_lowres", "v_lowres")
+    # coarse / fine / u / v, then the confidence heads a WC* model carries (chart_with_confidence.py:50-89); all of them
+    # ConvTranspose2d(512, C, 4, stride 2, pad 1), fused on Cout
+    names = ("ann_index_lowres", "index_uv_lowres", "u_lowres", "v_lowres") + tuple(h + "_lowres" for h, _ in spec.extra_heads)
     wt = torch.cat([sd[pp + n + ".weight"].float() for n in names], dim=1)     # [512, Ctot, 4, 4]
     bt = torch.cat([sd[pp + n + ".bias"].float() for n in names], dim=0)
     for py in range(2):

@@ -161,13 +161,13 @@ int dpb200_groupnorm_relu(const void* x, const float* gamma, const float* beta, 
 int dpb200_avgpool(const void* x, void* y, int32_t r, int32_t hw, int32_t c, const int32_t* n_valid, void* stream);
 
 /* interp2d (bilinear x2) of DensePoseChartPredictor.forward (densepose/modeling/predictors/chart.py:62-90).
- * low [R,2,2,cpad,S/2,S/2] fp32 — the four ConvTranspose output phases (py,px) as channel planes (channels
- * coarse[kc], fine[25], u[25], v[25]), the layout dpb200_conv2d writes with y_sc > 1 — -> four NCHW fp32
- * [R,C,2S,2S]. planar must be 1 (the NHWC variant of ABI 3 is gone). Bit-identical to ATen's CPU bilinear,
- * including its switch to the channels-last kernel when the output h + w <= 128 (the legacy 56x56 heads). */
-int dpb200_predictor_upsample(const float* low, int32_t r, int32_t s, int32_t cpad, int32_t kc,
-                              const int32_t* n_valid, float* coarse, float* fine, float* u, float* v,
-                              int32_t planar, void* stream);
+ * low [R,2,2,cpad,S/2,S/2] fp32 — the four ConvTranspose output phases (py,px) as channel planes, the layout
+ * dpb200_conv2d writes with y_sc > 1 — -> n NCHW fp32 tensors: out[i] is [R,ch[i],2S,2S] and takes the next ch[i]
+ * channels of low (the engine's order: coarse[kc], fine[25], u[25], v[25], then the confidence heads of a WC* model,
+ * chart_with_confidence.py:50-89). A NULL out[i] skips that head. Bit-identical to ATen's CPU bilinear, including its
+ * switch to the channels-last kernel when the output h + w <= 128 (the legacy 56x56 heads). */
+int dpb200_predictor_upsample(const float* low, int32_t r, int32_t s, int32_t cpad, const int32_t* n_valid,
+                              void* const* out, const int32_t* ch, int32_t n, void* stream);
 
 /* DensePoseResultExtractor (visualizer.py:10-56): per-box resize + argmax + U/V gather.
  * box_wh [D,2] = (max(int(w),1), max(int(h),1)); offsets [D+1] pixel prefix sums; labels int64 packed
@@ -195,6 +195,10 @@ typedef struct dpb200_model_config {
   int32_t min_size, max_size;
   float pixel_mean[3], pixel_std[3];
   int32_t input_rgb;        /* INPUT.FORMAT == "RGB"                                              */
+  int32_t extra_ch[5];      /* confidence heads a WC* model carries, in this order: sigma_2, kappa_u, kappa_v,
+                               fine_segm_confidence, coarse_segm_confidence (chart_with_confidence.py:50-89): channel count
+                               (25, 25, 25, 1, 1) or 0 when the head is absent. The reference builds these layers but its
+                               forward drops them (chart_with_confidence.py:91-109); the engine can emit them (f4). */
   int32_t strict;           /* 1: fp32-class numerics end to end — activations and weights as bf16 hi/lo pairs, three
                                tensor-core passes per product, fp32 accumulate (the weights handed to
                                dpb200_model_create must then be packed with three K segments per tap); the mode in
@@ -234,6 +238,8 @@ typedef struct dpb200_forward_io {
   void* v;                  /* [B*dets_per_image, 25, 4S, 4S]                                     */
   int32_t out_half;         /* != 0: the four DensePose tensors are written as IEEE fp16 (what the reference's
                              * `.half()` module returns, run.py:20-29); boxes and scores stay fp32         */
+  void* extra[5];           /* [B*dets_per_image, extra_ch[i], 4S, 4S] for the confidence heads the model carries (same
+                             * dtype as u / v), or NULL to skip a head                                      */
 } dpb200_forward_io;
 int dpb200_session_run(dpb200_session* s, const dpb200_forward_io* io, void* stream);
 /* enable != 0: dpb200_session_run captures its launch sequence into a CUDA graph the first time it sees an

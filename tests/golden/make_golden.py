@@ -31,6 +31,11 @@ EXTRA = {
     "densepose_rcnn_R_50_FPN_s1x__800x1333": ("densepose_rcnn_R_50_FPN_s1x", dict(height=800, width=1333, seed=1), False),
     "densepose_rcnn_R_101_FPN_s1x__1080p": ("densepose_rcnn_R_101_FPN_s1x", dict(height=1080, width=1920, seed=11), False),
     "densepose_rcnn_R_101_FPN_s1x__1080p_u8": ("densepose_rcnn_R_101_FPN_s1x", dict(height=1080, width=1920, seed=11), True),
+    # confidence variants: the reference builds sigma_2 / kappa_u / kappa_v / segm-confidence layers but its forward drops
+    # them (chart_with_confidence.py:91-109); the fixture also holds those layers applied to the reference's own head
+    # output (interp2d(layer(head_outputs)), as upstream DensePose emits them)
+    "densepose_rcnn_R_50_FPN_WC1_s1x": ("densepose_rcnn_R_50_FPN_WC1_s1x", dict(height=240, width=600, seed=3), False),
+    "densepose_rcnn_R_50_FPN_WC2M_s1x": ("densepose_rcnn_R_50_FPN_WC2M_s1x", dict(height=240, width=600, seed=3), False),
 }
 DP_KEYS = ["pred_densepose_coarse_segm", "pred_densepose_fine_segm", "pred_densepose_u", "pred_densepose_v"]
 N_LABELS = 16      # detections whose native-resolution part-label map is stored
@@ -84,9 +89,19 @@ def generate(name: str, config: str, image: dict, u8: bool, here: str):
     pred = build_reference(config)
     pred.load_state_dict(W.add_aliases(sd, spec), strict=True)
     img = make_image(image, u8)
+    captured = {}
+    predictor = pred.model.roi_heads.densepose_predictor
+    hook = predictor.register_forward_hook(lambda mod, inp, outp: captured.update(head=inp[0]))
     with torch.no_grad():
         out = pred(img)
+        hook.remove()
+        for head, _ in spec.extra_heads:      # every detection survives detector_postprocess here (asserted below)
+            out["pred_densepose_" + head] = predictor.interp2d(getattr(predictor, head + "_lowres")(captured["head"]))
+            assert len(out["pred_densepose_" + head]) == len(out["scores"])
     fx = summarize(out)
+    for head, _ in spec.extra_heads:
+        fx["pred_densepose_" + head + ".sample16"] = out["pred_densepose_" + head][:N_SAMPLE, :, ::8, ::8].half()
+    fx["extra_heads"] = [h for h, _ in spec.extra_heads]
     fx["config"] = config
     fx["image"] = dict(image)
     fx["uint8"] = u8

@@ -120,3 +120,41 @@ def test_run_py_video_batches_match_frame_by_frame(scripted, tmp_path):
     assert n == 7 and len(got) == 7               # two full batches of 3 through the pipeline + a tail of 1
     for a, b in zip(got, want):
         assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_confidence_model_emits_its_extra_heads():
+    """A WC* model: the scripted module returns the reference's eight keys plus one
+    pred_densepose_<head> per confidence layer the config carries (chart_with_confidence.py:50-89), each the fp32
+    ConvTranspose2d + bilinear x2 of the engine's own head output."""
+    import torch.nn.functional as F
+
+    from _util import nchw, rel_l2
+    from densepose_torchscript_b200.config import BUILTIN
+    from densepose_torchscript_b200.engine import Engine
+    from densepose_torchscript_b200.predictor import DensePoseB200Predictor
+    name = "densepose_rcnn_R_50_FPN_WC2M_s1x"
+    spec = BUILTIN[name]
+    assert [h for h, _ in spec.extra_heads] == ["sigma_2", "kappa_u", "kappa_v", "fine_segm_confidence", "coarse_segm_confidence"]
+    sd = W.make_state_dict(O.SPECS[name], 0)
+    pred = DensePoseB200Predictor(spec, W.add_aliases(sd, O.SPECS[name])).eval()
+    buf = io.BytesIO()
+    torch.jit.save(torch.jit.script(pred), buf)
+    buf.seek(0)
+    model = torch.jit.load(buf).eval().cuda()
+    img = W.synthetic_image(200, 320, seed=11)
+    out = model(img)
+    d = len(out["scores"])
+    assert d > 0
+    for head, ch in spec.extra_heads:
+        assert out["pred_densepose_" + head].shape == (d, ch, 112, 112)
+    eng = Engine(spec, sd)
+    ref = eng.forward_batch(img[None])[0]
+    for k in out:
+        assert torch.equal(out[k], ref[k]), k
+    sess = eng.session(1, 200, 320, False)
+    head_out = nchw(sess.tap("dp_head"))[:d]
+    for head, _ in spec.extra_heads:
+        p = "roi_heads.densepose_predictor." + head + "_lowres"
+        low = F.conv_transpose2d(head_out, sd[p + ".weight"].to(torch.bfloat16).float(), sd[p + ".bias"], stride=2, padding=1)
+        want = F.interpolate(low, scale_factor=2.0, mode="bilinear", align_corners=False)
+        assert rel_l2(out["pred_densepose_" + head], want) < 2e-3, head

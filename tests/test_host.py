@@ -60,7 +60,8 @@ def test_builtin_specs_match_oracle_specs():
     for k, s in BUILTIN.items():
         o = O.SPECS[k]
         for f in ("depth", "head", "decoder_on", "pooler_res", "coarse_ch", "score_thresh", "nms_test", "dets_per_image",
-                  "min_size", "max_size", "rpn_pre_topk", "rpn_post_topk", "rpn_nms", "pixel_mean", "pixel_std", "input_format"):
+                  "min_size", "max_size", "rpn_pre_topk", "rpn_post_topk", "rpn_nms", "pixel_mean", "pixel_std", "input_format",
+                  "uv_confidence", "segm_confidence", "extra_heads"):
             assert getattr(s, f) == getattr(o, f), (k, f)
 
 
