@@ -92,7 +92,7 @@ class ModelConfig(C.Structure):
         ("score_thresh", f32), ("nms_test", f32), ("rpn_nms", f32),
         ("dets_per_image", i32), ("rpn_pre_topk", i32), ("rpn_post_topk", i32),
         ("min_size", i32), ("max_size", i32),
-        ("pixel_mean", f32 * 3), ("pixel_std", f32 * 3), ("input_rgb", i32), ("extra_ch", i32 * 5), ("strict", i32),
+        ("pixel_mean", f32 * 3), ("pixel_std", f32 * 3), ("input_rgb", i32), ("extra_ch", i32 * 5), ("resize_variant", i32), ("strict", i32),
     ]
 
 

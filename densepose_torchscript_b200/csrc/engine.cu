@@ -227,7 +227,7 @@ int build_plan(dpb200_session* s) {
     for (int i = 0; i < 3; ++i) { p.mean[i] = cfg.pixel_mean[i]; p.std[i] = cfg.pixel_std[i]; }
     p.dst = reinterpret_cast<bf16*>(x0.p); p.Hp = Hp; p.Wx = s->Wx;
     p.dst_lo = reinterpret_cast<bf16*>(x0.p2);
-    p.variant = 0; p.tables = nullptr;
+    p.variant = cfg.resize_variant ? 1 : 0; p.tables = nullptr;
     dpb200_session* ss = s;
     // (allocated for every session so that dpb200_session_workspace_bytes does not depend on the input type)
     int2* tab = (int2*)b.alloc((size_t)(1 + s->Hr + s->Wr) * sizeof(int2));

@@ -155,7 +155,7 @@ class Engine:
 
     def __init__(self, spec: ModelSpec, state_dict: Optional[Dict[str, torch.Tensor]] = None,
                  packed: Optional[Dict[str, Packed]] = None, device: Optional[torch.device] = None,
-                 use_graph: bool = True, max_sessions: int = 4, strict: bool = False):
+                 use_graph: bool = True, max_sessions: int = 4, strict: bool = False, resize_variant: int = 0):
         """strict: fp32-class numerics end to end (activations and weights as bf16 hi/lo pairs, three tensor-core passes
         per product, fp32 accumulate; `packed` weights must then come from pack_state_dict(..., strict=True)) — the mode
         in which proposals, NMS keep lists, detection counts and label maps are compared with the reference by index.
@@ -183,6 +183,7 @@ class Engine:
             cfg.pixel_mean[i] = spec.pixel_mean[i]; cfg.pixel_std[i] = spec.pixel_std[i]
         cfg.input_rgb = int(spec.input_format == "RGB")
         cfg.strict = int(strict)
+        cfg.resize_variant = int(resize_variant)     # 0: ATen's multi-threaded float resize kernel, 1: its single-threaded one
         heads = dict(spec.extra_heads)
         for i, name in enumerate(EXTRA_HEAD_ORDER):
             cfg.extra_ch[i] = heads.get(name, 0)

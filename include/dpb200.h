@@ -199,6 +199,9 @@ typedef struct dpb200_model_config {
                                fine_segm_confidence, coarse_segm_confidence (chart_with_confidence.py:50-89): channel count
                                (25, 25, 25, 1, 1) or 0 when the head is absent. The reference builds these layers but its
                                forward drops them (chart_with_confidence.py:91-109); the engine can emit them (f4). */
+  int32_t resize_variant;   /* float images: which of ATen's two CPU bilinear kernels the resize reproduces bit for bit
+                               (dpb200_preprocess_args.variant): 0 = a reference running with > 1 intra-op threads,
+                               1 = a single-threaded one. uint8 images have one kernel.                       */
   int32_t strict;           /* 1: fp32-class numerics end to end — activations and weights as bf16 hi/lo pairs, three
                                tensor-core passes per product, fp32 accumulate (the weights handed to
                                dpb200_model_create must then be packed with three K segments per tap); the mode in

@@ -576,7 +576,7 @@ def test_predictor_upsample_is_bit_exact(ops, S, kc):
     lin = torch.zeros(3, S, S, cpad)
     lin[..., :C] = low.permute(0, 2, 3, 1)
     lin = lin.view(3, S // 2, 2, S // 2, 2, cpad).permute(0, 2, 4, 5, 1, 3)    # [R, py, px, c, S/2, S/2]
-    outs = ops.predictor_upsample(lin.cuda().contiguous(), kc)
+    outs = ops.predictor_upsample(lin.cuda().contiguous(), (kc, 25, 25, 25))
     torch.cuda.synchronize()
     got = torch.cat([o.cpu() for o in outs], dim=1)
     assert torch.equal(got, ref), float((got - ref).abs().max())

@@ -3,7 +3,7 @@
 #   1. launch list: per-launch device time of one step          -> <tag>_ncu_launches.csv
 #   2. SpeedOfLight / memory / launch / occupancy sections       -> <tag>_ncu_step_sections.csv (via ncu_summarise.py)
 #   3. --set full + source of one 512->512 3x3 head conv         -> <tag>_ncu_conv_head_full_raw.csv, _source_top.csv
-tag=${1:-r01}
+tag=${1:-r02}
 only=${2:-all}
 o=gpurun_out
 mkdir -p $o
@@ -14,6 +14,13 @@ ncu --profile-from-start off --section SpeedOfLight --section MemoryWorkloadAnal
     --clock-control none -f -o $o/step_sections python tools/prof_step.py 2> $o/ops2.txt > /dev/null
 ncu -i $o/step_sections.ncu-rep --page raw --csv > $o/step_sections_raw.csv
 python tools/ncu_summarise.py $o/step_sections_raw.csv $o/ops.txt $o/${tag}_ncu_step_sections.csv
+# stamp: the hash of the CUDA sources this capture was taken from (bench.py refuses a capture whose stamp is stale)
+python - "$o/${tag}_ncu_step_sections.meta.json" <<'P'
+import json, sys
+sys.path.insert(0, ".")
+import bench
+json.dump({"csrc_sha": bench.csrc_sha(), "command": "tools/profile_round.sh", "workload": "bench.py default (configs[1])"}, open(sys.argv[1], "w"))
+P
 rm -f $o/step_sections.ncu-rep
 [ "$only" = sections ] && exit 0
 ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:conv_igemm -s 83 -c 1 \
