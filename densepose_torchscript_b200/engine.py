@@ -376,12 +376,15 @@ class HostPipeline:
             sess.stream.synchronize()
         self.extract_d2h_bytes = total * (lab_b + 8)
         self.last_d2h_bytes = self.small_d2h_bytes + self.extract_d2h_bytes
+        # plain Python ints for the per-detection views (indexing a tensor per detection costs more than the kernel)
+        whl, offl = wh.tolist(), offsets.tolist()
+        labels_h, uv_h = ex_host
         out, k = [], 0
         for b in range(sess.batch):
             dens = []
             for _ in range(cnt[b]):
-                w, h, o = int(wh[k, 0]), int(wh[k, 1]), int(offsets[k])
-                dens.append({"labels": ex_host[0][o:o + h * w].view(h, w), "uv": ex_host[1][2 * o:2 * o + 2 * h * w].view(2, h, w)})
+                (w, h), o = whl[k], offl[k]
+                dens.append({"labels": labels_h[o:o + h * w].view(h, w), "uv": uv_h[2 * o:2 * o + 2 * h * w].view(2, h, w)})
                 k += 1
             out.append({"image_size": torch.tensor([sess.h0, sess.w0], dtype=torch.int64),
                         "pred_boxes": boxes[b, :cnt[b]], "scores": scores[b, :cnt[b]],
