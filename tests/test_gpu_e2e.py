@@ -138,6 +138,32 @@ def test_full_size_properties(s1x):
     assert len(r0["scores"]) == r0["pred_densepose_u"].shape[0]
 
 
+def test_portrait_image_swapped_clip_quirk_on_the_device(s1x):
+    """A portrait image (300x200 -> 1200x800 -> padded 1216x800): quirk 1 clips proposal x to [0, H_pad] and y to
+    [0, W_pad] (rpn.py:339 vs structures.py:107-112); on a portrait input that lets boxes run past the image on the
+    right. Engine vs the bf16 oracle on the same image: geometry, the clip extents, and matched detections."""
+    eng, sd = s1x
+    spec = O.SPECS["densepose_rcnn_R_50_FPN_s1x"]
+    img = W.synthetic_image(300, 200, seed=5)
+    taps = {}
+    ref = O.forward(img, sd, spec, mode="bf16", taps=taps)
+    sess = eng.session(1, 300, 200, False)
+    sess.run(img[None].cuda().contiguous())
+    torch.cuda.synchronize()
+    assert (sess.hr, sess.wr, sess.hp, sess.wp) == (1200, 800, 1216, 800)
+    n = int(sess.tap("proposal_count").view(-1)[0])
+    pb = sess.tap("proposal_boxes")[0, :n, :, 0].float().cpu()
+    ref_pb = taps["proposals"]["proposal_boxes"]
+    assert float(pb[:, 0::2].max()) <= 1216.0 and float(pb[:, 1::2].max()) <= 800.0      # x <= H_pad, y <= W_pad
+    assert float(pb[:, 0::2].max()) > 800.0 or float(ref_pb[:, 0::2].max()) <= 800.0     # the quirk bites when it does in the oracle
+    assert abs(n - len(ref_pb)) <= 30
+    res = sess.results()[0]
+    assert torch.equal(res["image_size"].cpu(), ref["image_size"])
+    ia, ib = match_detections(res["pred_boxes"], ref["pred_boxes"], 2.0)
+    assert len(ia) >= 0.85 * len(ref["scores"])
+    assert float((res["scores"][ia].cpu() - ref["scores"][ib]).abs().max()) < 1e-2
+
+
 def test_uint8_input_session(s1x):
     """uint8 frames (run.py:33-36) take ATen's fixed-point resize inside the session: the stem input equals the
     per-op kernel's (bit-exact against ATen in test_gpu_ops) and differs from the float path's, whose resize rounds
