@@ -164,6 +164,26 @@ def test_portrait_image_swapped_clip_quirk_on_the_device(s1x):
     assert float((res["scores"][ia].cpu() - ref["scores"][ib]).abs().max()) < 1e-2
 
 
+@pytest.mark.parametrize("h0,w0", [(64, 64), (33, 257), (257, 33), (101, 37)])
+def test_ragged_image_sizes_run_like_the_oracle(s1x, h0, w0):
+    """Extreme aspect ratios and tiny inputs (the reference takes any H x W): the resize geometry, the pyramid sizes
+    (p6 = ceil(p5 / 2) down to a single row / column) and the result shapes follow the oracle; detections match."""
+    eng, sd = s1x
+    spec = O.SPECS["densepose_rcnn_R_50_FPN_s1x"]
+    img = W.synthetic_image(h0, w0, seed=h0 + w0)
+    ref = O.forward(img, sd, spec, mode="bf16")
+    res = eng.forward_batch(img[None])[0]
+    torch.cuda.synchronize()
+    assert torch.equal(res["image_size"].cpu(), ref["image_size"]) and res["image_size"].tolist() == [h0, w0]
+    assert abs(len(res["scores"]) - len(ref["scores"])) <= max(3, len(ref["scores"]) // 10)
+    assert res["pred_densepose_u"].shape[1:] == (25, 112, 112)
+    if len(ref["scores"]):
+        ia, ib = match_detections(res["pred_boxes"], ref["pred_boxes"], 2.0 * max(h0, w0) / 200 + 0.5)
+        assert len(ia) >= 0.7 * len(ref["scores"])
+        bx = res["pred_boxes"]
+        assert float(bx.min()) >= 0 and float(bx[:, 0::2].max()) <= w0 and float(bx[:, 1::2].max()) <= h0
+
+
 def test_uint8_input_session(s1x):
     """uint8 frames (run.py:33-36) take ATen's fixed-point resize inside the session: the stem input equals the
     per-op kernel's (bit-exact against ATen in test_gpu_ops) and differs from the float path's, whose resize rounds
