@@ -158,3 +158,11 @@ def test_confidence_model_emits_its_extra_heads():
         low = F.conv_transpose2d(head_out, sd[p + ".weight"].to(torch.bfloat16).float(), sd[p + ".bias"], stride=2, padding=1)
         want = F.interpolate(low, scale_factor=2.0, mode="bilinear", align_corners=False)
         assert rel_l2(out["pred_densepose_" + head], want) < 2e-3, head
+    # and through the host pipeline (count-aware D2H of every head)
+    from densepose_torchscript_b200.engine import HostPipeline
+    pipe = HostPipeline(eng, 1, 200, 320, False, depth=1)
+    assert pipe.submit(img[None]) is None
+    (got,) = pipe.drain()
+    for k in ref:
+        assert torch.equal(got[0][k], ref[k].cpu()), k
+    pipe.close()
