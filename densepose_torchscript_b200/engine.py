@@ -240,26 +240,28 @@ class Engine:
 
 class HostPipeline:
     """Host-in / host-out serving loop: `depth` sessions of one shape, each with its own stream and pinned
-    staging buffers, so the PCIe copies of one batch overlap the kernels of the next.
+    staging buffers, so the PCIe copies of one batch overlap the kernels of the next and the host never blocks on a
+    copy it has just issued.
 
         pipe = HostPipeline(engine, batch, h0, w0)
         for frames in batches:            # frames: [B,H,W,3] host tensor (pinned or not)
-            done = pipe.submit(frames)    # results of the batch submitted `depth` calls ago (or None)
-        tail = pipe.drain()
+            done = pipe.submit(frames)    # results of the batch submitted `depth + 1` calls ago (or None)
+        tail = pipe.drain()               # everything still in flight, oldest first
 
-    submit() enqueues H2D copy -> forward -> D2H of boxes / scores / counts on the slot's stream. When a slot is
-    collected (the submit() `depth` calls later, or drain()) the DensePose tensors come back COUNT-AWARE: the rows are
-    packed by `det_offsets` on the device, so only the `dp_total` rows that hold detections cross PCIe, not the
-    B x dets_per_image capacity (386 MB per image at 100 detections, 3.9 MB per detection). Those copies run on the
-    collected slot's stream while the other slots' forwards keep the GPU busy.
+    submit(k) does three things, in this order:
+      1. the slot it is about to reuse ran batch k - depth: its forward has finished, its boxes / scores / counts are on
+         the host, so the DensePose tensors are copied back COUNT-AWARE — the rows are packed by `det_offsets` on the
+         device, only the `dp_total` rows that hold detections cross PCIe, not the B x dets_per_image capacity (386 MB
+         per image at 100 detections, 3.9 MB per detection). The copies are enqueued on the slot's stream, not waited for;
+      2. batch k is enqueued behind them (H2D copy -> forward -> D2H of boxes / scores / counts);
+      3. the copies issued by the PREVIOUS call have had a whole call to finish: they are waited for and returned.
 
-    Lifetime of returned tensors: they are views of pinned host buffers owned by the pipeline. Two result sets
-    rotate, and a call never writes into the set the previous call handed out: results returned by one submit() stay
-    valid until the NEXT submit() has returned; drain() reuses both sets, so consume (or copy) earlier results before
-    calling it. Copy what must live longer.
+    Lifetime of returned tensors: they are views of pinned host buffers owned by the pipeline; `depth + 1` result sets
+    rotate, so what one submit() returns stays valid until the NEXT submit() has returned, and everything drain()
+    returns is valid together. Copy what must live longer.
 
     extract=True is the run.py flow (run.py:33-57 + visualizer.py:46-56) as a pipeline: only boxes / scores /
-    counts come back after the forward; when a slot is collected, the per-box resample + part argmax + U/V gather
+    counts come back after the forward; in step 1 the per-box resample + part argmax + U/V gather
     (`dpb200_dp_resample`) runs on the device over that batch's detections and only `labels` (uint8, or int64
     like the reference with labels_u8=False) and `uv` at box resolution cross PCIe. Each result dict then holds
     pred_boxes, scores, boxes_xywh and `densepose` = [{'labels': [h,w], 'uv': [2,h,w]} per detection].
@@ -271,8 +273,8 @@ class HostPipeline:
         self.extract, self.labels_u8 = extract, labels_u8
         if extract and out_half:
             raise ValueError("extract=True reads the fp32 DensePose tensors on the device; out_half is for full outputs")
-        self.extract_d2h_bytes = 0          # bytes of the last collected extraction (data dependent)
-        self.last_d2h_bytes = 0             # bytes the last collected batch moved device -> host (count-aware)
+        self.extract_d2h_bytes = 0          # bytes of the last returned extraction (data dependent)
+        self.last_d2h_bytes = 0             # bytes the last RETURNED batch moved device -> host (count-aware)
         self.slots = []
         dt = torch.uint8 if src_u8 else torch.float32
         with torch.cuda.device(engine.device):
@@ -284,17 +286,19 @@ class HostPipeline:
                 small_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in small_dev]
                 self.slots.append(dict(sess=sess, dev_in=dev_in, host_in=host_in, small_dev=small_dev,
                                        small_host=small_host, done=torch.cuda.Event(), busy=False,
-                                       ex_dev=None, ex_host=None))
-            # two rotating result sets for the big tensors (full capacity, pinned): the set handed to the caller by one
-            # call is never the one the next call fills
+                                       ex_dev=[None, None], ex_host=[None, None], ex_flip=0))
+            # depth + 1 rotating result sets for the big tensors (full capacity, pinned): up to depth batches in the
+            # slots plus one whose copy has been issued can be in flight, and a returned set is not refilled before the
+            # next submit() has returned
             s0 = self.slots[0]["sess"]
             self.big_dev_names = ("coarse", "fine", "u", "v") + tuple(n for n, _ in engine.spec.extra_heads)
             self.sets = []
             if not extract:
-                for _ in range(2):
+                for _ in range(depth + 1):
                     self.sets.append([torch.empty(self._big(s0, n).shape, dtype=self._big(s0, n).dtype).pin_memory()
                                       for n in self.big_dev_names])
         self._set = 0
+        self._pending = None                # ticket of the batch whose D2H has been issued but not yet returned
         self.h2d_bytes = self.slots[0]["host_in"].numel() * self.slots[0]["host_in"].element_size()
         self.small_d2h_bytes = sum(t.numel() * t.element_size() for t in self.slots[0]["small_host"])
         self.row_bytes = 0 if extract else sum(t[0].numel() * t.element_size() for t in self.sets[0])
@@ -315,40 +319,35 @@ class HostPipeline:
                     del self.engine._sessions[k]
         self.slots = []
         self.sets = []
+        self._pending = None
 
-    def _collect(self, sl) -> Optional[List[Dict[str, torch.Tensor]]]:
+    # ---- step 1: the slot's forward is done -> enqueue the (count-aware) copies of its results, do not wait
+    def _issue(self, sl) -> Optional[dict]:
         if not sl["busy"]:
             return None
-        sl["done"].synchronize()
+        sl["done"].synchronize()            # forward + small copies, enqueued `depth` calls ago
         sl["busy"] = False
         # boxes / scores / counts leave the slot's staging buffers (the slot is re-enqueued right after this)
         boxes, scores, counts, offs = [t.clone() for t in sl["small_host"]]
+        sess = sl["sess"]
+        ticket = dict(sess=sess, boxes=boxes, scores=scores, counts=counts, offs=offs, event=torch.cuda.Event())
         if self.extract:
-            return self._collect_extracted(sl, boxes, scores, counts)
-        sess = sl["sess"]
-        n = int(offs[sess.batch])                      # dp_total: rows that hold detections
-        host = self.sets[self._set]
-        self._set ^= 1
-        if n:
-            with torch.cuda.device(self.engine.device), torch.cuda.stream(sess.stream):
-                for hbuf, name in zip(host, self.big_dev_names):
-                    hbuf[:n].copy_(self._big(sess, name)[:n], non_blocking=True)
-            sess.stream.synchronize()
-        self.last_d2h_bytes = self.small_d2h_bytes + n * self.row_bytes
-        keys = ("coarse_segm", "fine_segm", "u", "v") + self.big_dev_names[4:]
-        out = []
-        for b in range(sess.batch):
-            d, o = int(counts[b]), int(offs[b])
-            res = {"image_size": torch.tensor([sess.h0, sess.w0], dtype=torch.int64),
-                   "pred_boxes": boxes[b, :d], "scores": scores[b, :d], "pred_classes": torch.zeros(d, dtype=torch.int64)}
-            for key, hbuf in zip(keys, host):
-                res["pred_densepose_" + key] = hbuf[o:o + d]
-            out.append(res)
-        return out
+            self._issue_extraction(sl, ticket)
+        else:
+            n = int(offs[sess.batch])                      # dp_total: rows that hold detections
+            host = self.sets[self._set]
+            self._set = (self._set + 1) % len(self.sets)
+            if n:
+                with torch.cuda.device(self.engine.device), torch.cuda.stream(sess.stream):
+                    for hbuf, name in zip(host, self.big_dev_names):
+                        hbuf[:n].copy_(self._big(sess, name)[:n], non_blocking=True)
+            ticket.update(host=host, bytes=self.small_d2h_bytes + n * self.row_bytes)
+        ticket["event"].record(sess.stream)
+        return ticket
 
-    def _collect_extracted(self, sl, boxes, scores, counts) -> List[Dict[str, object]]:
+    def _issue_extraction(self, sl, ticket):
         from . import ops
-        sess = sl["sess"]
+        sess, boxes, counts = ticket["sess"], ticket["boxes"], ticket["counts"]
         dev = self.engine.device
         cnt = [int(c) for c in counts]
         # packed detection order = the packed DensePose rows (det_offsets)
@@ -357,13 +356,15 @@ class HostPipeline:
         total = int(offsets[-1])
         lab_dt = torch.uint8 if self.labels_u8 else torch.int64
         lab_b = 1 if self.labels_u8 else 8
-        ex_dev, ex_host = sl["ex_dev"], sl["ex_host"]
+        flip = sl["ex_flip"]                               # two buffer sets per slot: what was returned stays intact
+        sl["ex_flip"] ^= 1
+        ex_dev, ex_host = sl["ex_dev"][flip], sl["ex_host"][flip]
         if ex_dev is None or ex_dev[0].numel() < total:
             cap = max(int(total * 1.25), 1 << 20)
             with torch.cuda.device(dev):
                 ex_dev = (torch.empty(cap, dtype=lab_dt, device=dev), torch.empty(2 * cap, dtype=torch.float32, device=dev))
             ex_host = (torch.empty(cap, dtype=lab_dt).pin_memory(), torch.empty(2 * cap, dtype=torch.float32).pin_memory())
-            sl["ex_dev"], sl["ex_host"] = ex_dev, ex_host
+            sl["ex_dev"][flip], sl["ex_host"][flip] = ex_dev, ex_host
         n = int(sum(cnt))
         if n and total:
             with torch.cuda.device(dev), torch.cuda.stream(sess.stream):
@@ -373,31 +374,53 @@ class HostPipeline:
                                      ex_dev[0], ex_dev[1], stream=C.c_void_p(sess.stream.cuda_stream))
                 ex_host[0][:total].copy_(ex_dev[0][:total], non_blocking=True)
                 ex_host[1][:2 * total].copy_(ex_dev[1][:2 * total], non_blocking=True)
-            sess.stream.synchronize()
-        self.extract_d2h_bytes = total * (lab_b + 8)
-        self.last_d2h_bytes = self.small_d2h_bytes + self.extract_d2h_bytes
-        # plain Python ints for the per-detection views (indexing a tensor per detection costs more than the kernel)
-        whl, offl = wh.tolist(), offsets.tolist()
-        labels_h, uv_h = ex_host
-        out, k = [], 0
+            ticket["keep"] = (wh_d, off_d)                # alive until the kernel has run
+        ticket.update(cnt=cnt, boxes_xywh=boxes_xywh, wh=wh, offsets=offsets, ex_host=ex_host,
+                      bytes=self.small_d2h_bytes + total * (lab_b + 8), ex_bytes=total * (lab_b + 8))
+
+    # ---- step 3: wait for copies issued one call ago, build the reference-format result dicts over the pinned buffers
+    def _finish(self, ticket) -> Optional[List[Dict[str, object]]]:
+        if ticket is None:
+            return None
+        ticket["event"].synchronize()
+        sess, boxes, scores = ticket["sess"], ticket["boxes"], ticket["scores"]
+        self.last_d2h_bytes = ticket["bytes"]
+        out = []
+        if self.extract:
+            self.extract_d2h_bytes = ticket["ex_bytes"]
+            cnt, boxes_xywh = ticket["cnt"], ticket["boxes_xywh"]
+            # plain Python ints for the per-detection views (indexing a tensor per detection costs more than the kernel)
+            whl, offl = ticket["wh"].tolist(), ticket["offsets"].tolist()
+            labels_h, uv_h = ticket["ex_host"]
+            k = 0
+            for b in range(sess.batch):
+                dens = []
+                for _ in range(cnt[b]):
+                    (w, h), o = whl[k], offl[k]
+                    dens.append({"labels": labels_h[o:o + h * w].view(h, w), "uv": uv_h[2 * o:2 * o + 2 * h * w].view(2, h, w)})
+                    k += 1
+                out.append({"image_size": torch.tensor([sess.h0, sess.w0], dtype=torch.int64),
+                            "pred_boxes": boxes[b, :cnt[b]], "scores": scores[b, :cnt[b]],
+                            "boxes_xywh": boxes_xywh[k - cnt[b]:k], "densepose": dens})
+            return out
+        counts, offs, host = ticket["counts"].tolist(), ticket["offs"].tolist(), ticket["host"]
+        keys = ("coarse_segm", "fine_segm", "u", "v") + self.big_dev_names[4:]
         for b in range(sess.batch):
-            dens = []
-            for _ in range(cnt[b]):
-                (w, h), o = whl[k], offl[k]
-                dens.append({"labels": labels_h[o:o + h * w].view(h, w), "uv": uv_h[2 * o:2 * o + 2 * h * w].view(2, h, w)})
-                k += 1
-            out.append({"image_size": torch.tensor([sess.h0, sess.w0], dtype=torch.int64),
-                        "pred_boxes": boxes[b, :cnt[b]], "scores": scores[b, :cnt[b]],
-                        "boxes_xywh": boxes_xywh[k - cnt[b]:k], "densepose": dens})
+            d, o = counts[b], offs[b]
+            res = {"image_size": torch.tensor([sess.h0, sess.w0], dtype=torch.int64),
+                   "pred_boxes": boxes[b, :d], "scores": scores[b, :d], "pred_classes": torch.zeros(d, dtype=torch.int64)}
+            for key, hbuf in zip(keys, host):
+                res["pred_densepose_" + key] = hbuf[o:o + d]
+            out.append(res)
         return out
 
     def submit(self, images: torch.Tensor, bgr: bool = True):
-        """Enqueue one host batch; returns the finished results of the slot being reused (None at start-up).
-        A pinned `images` tensor is copied to the device directly (the caller keeps it unchanged until the
-        results come back); pageable memory goes through the slot's pinned staging buffer first."""
+        """Enqueue one host batch; returns the oldest finished batch (None while the pipeline fills: the first
+        `depth + 1` calls). A pinned `images` tensor is copied to the device directly (the caller keeps it unchanged
+        until the results come back); pageable memory goes through the slot's pinned staging buffer first."""
         sl = self.slots[self._next]
         self._next = (self._next + 1) % self.depth
-        prev = self._collect(sl)
+        ticket = self._issue(sl)
         src = images
         if not images.is_pinned():
             sl["host_in"].copy_(images)
@@ -410,17 +433,20 @@ class HostPipeline:
                 hbuf.copy_(dbuf, non_blocking=True)
             sl["done"].record(sess.stream)
         sl["busy"] = True
+        prev = self._finish(self._pending)
+        self._pending = ticket
         return prev
 
     def drain(self) -> List[List[Dict[str, torch.Tensor]]]:
-        """Collects every batch still in flight, oldest first. With full outputs the two rotating result sets can hold
-        two batches: draining more than two in-flight batches copies the older ones out of the pinned sets."""
+        """Returns every batch still in flight, oldest first (all valid together: depth + 1 result sets)."""
         out = []
+        r = self._finish(self._pending)
+        self._pending = None
+        if r is not None:
+            out.append(r)
         for i in range(self.depth):
             sl = self.slots[(self._next + i) % self.depth]
-            r = self._collect(sl)
+            r = self._finish(self._issue(sl))
             if r is not None:
-                if not self.extract and len(out) >= 1 and self.depth > 2:
-                    out[-1] = [{k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in d.items()} for d in out[-1]]
                 out.append(r)
         return out

@@ -247,18 +247,20 @@ def test_pipelined_extractor_matches_the_extractor_on_full_outputs(s1x):
 
 def test_pipeline_results_survive_the_next_submit_and_copies_are_count_aware(s1x):
     """HostPipeline with DISTINCT images per batch and a consumer that reads results late: what submit() returns stays
-    valid until the next call that returns results (two rotating pinned result sets; round 1 overwrote them from the
+    valid until the NEXT submit() has returned (depth + 1 rotating pinned result sets; round 1 overwrote them from the
     same call). The DensePose rows come back count-aware: only the rows that hold detections cross PCIe."""
     from densepose_torchscript_b200.engine import HostPipeline
     eng, _ = s1x
     batches = [torch.stack([W.synthetic_image(240, 600, seed=20 + 2 * i), W.synthetic_image(240, 600, seed=21 + 2 * i)])
-               for i in range(4)]
+               for i in range(6)]
     want = [[{k: v.cpu() for k, v in r.items()} for r in eng.forward_batch(b)] for b in batches]
     pipe = HostPipeline(eng, 2, 240, 600, False, depth=2)
     got = []
     held = None
+    returned = []
     for b in batches:
-        r = pipe.submit(b)                       # enqueues the next batch into the slot whose results `held` came from
+        r = pipe.submit(b)                       # issues the next copies and enqueues the next batch
+        returned.append(r is not None)
         if held is not None:
             torch.cuda.synchronize()             # the new batch has certainly run: `held` must still be intact
             got.append([{k: v.clone() for k, v in d.items()} for d in held])
@@ -270,7 +272,8 @@ def test_pipeline_results_survive_the_next_submit_and_copies_are_count_aware(s1x
         got.append([{k: v.clone() for k, v in d.items()} for d in held])
     tail = pipe.drain()
     got += [[{k: v.clone() for k, v in d.items()} for d in r] for r in tail]
-    assert len(got) == 4
+    assert returned == [False, False, False, True, True, True]      # results come back depth + 1 calls later
+    assert len(got) == 6 and len(tail) == 3
     for g, w in zip(got, want):
         for a, b in zip(g, w):
             assert len(a["scores"]) == len(b["scores"]) > 0
