@@ -388,6 +388,51 @@ def run_ours(a):
         del hbuf, dbuf
         return out
 
+    # ---- p50 batch-1 latency (BASELINE.json's second metric): one image, host in -> host out, synchronous
+    def measure_latency(engine, full_variants):
+        def p50_of(pipe, img):
+            t_ = []
+            for i in range(5 + 30):
+                t0 = time.perf_counter()
+                pipe.submit(img)
+                pipe.drain()
+                if i >= 5:
+                    t_.append((time.perf_counter() - t0) * 1e3)
+            t_.sort()
+            return t_[len(t_) // 2], t_[int(len(t_) * 0.9)]
+
+        pipe1 = HostPipeline(engine, 1, H, W, False, depth=1)
+        one = host[:1].clone().pin_memory()
+        p50, p90 = p50_of(pipe1, one)
+        ts_dev = []
+        s1, dev1 = pipe1.slots[0]["sess"], pipe1.slots[0]["dev_in"]
+        for i in range(3 + 30):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            s1.run(dev1)
+            ev1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts_dev.append(ev0.elapsed_time(ev1))
+        ts_dev.sort()
+        out = {"p50_ms": p50, "p90_ms": p90, "device_only_p50_ms": ts_dev[len(ts_dev) // 2], "samples": 30,
+               "d2h_bytes": pipe1.last_d2h_bytes, "detections": int(s1.det_count.cpu().sum()),
+               "note": "batch 1, pinned host image in, all outputs back in pinned host memory, wall clock around submit+drain"}
+        pipe1.close()
+        del pipe1
+        if full_variants:
+            pipe_h = HostPipeline(engine, 1, H, W, False, depth=1, out_half=True)
+            out["p50_ms_half_outputs"] = p50_of(pipe_h, one)[0]
+            pipe_h.close()
+            del pipe_h
+        one_u8 = one.round().clamp(0, 255).to(torch.uint8).pin_memory()
+        pipe_x = HostPipeline(engine, 1, H, W, True, depth=1, extract=True)
+        out["p50_ms_extracted"] = p50_of(pipe_x, one_u8)[0]
+        pipe_x.close()
+        del pipe_x
+        torch.cuda.empty_cache()
+        return out
+
     sampler = ClockSampler(local) if rank == 0 else None
     sess, ms_dev, total_dets, clocks = measure_device(eng, sampler)
     dets = int(sess.det_count.cpu().sum())
@@ -424,51 +469,14 @@ def run_ours(a):
         if not a.no_e2e:
             realistic["e2e"] = measure_e2e(eng_r)
             realistic["e2e"]["variants"] = {"extracted": measure_e2e(eng_r, extract=True)}
+        if world == 1 and not a.no_latency:
+            realistic["latency_batch1"] = measure_latency(eng_r, full_variants=False)
         del sess_r, eng_r
         torch.cuda.empty_cache()
 
-    # ---- p50 batch-1 latency (BASELINE.json's second metric): one image, host in -> host out, synchronous
     lat = None
     if world == 1 and not a.no_latency:
-        def p50_of(pipe, img):
-            t_ = []
-            for i in range(5 + 30):
-                t0 = time.perf_counter()
-                pipe.submit(img)
-                pipe.drain()
-                if i >= 5:
-                    t_.append((time.perf_counter() - t0) * 1e3)
-            t_.sort()
-            return t_[len(t_) // 2], t_[int(len(t_) * 0.9)]
-
-        pipe1 = HostPipeline(eng, 1, H, W, False, depth=1)
-        one = host[:1].clone().pin_memory()
-        p50, p90 = p50_of(pipe1, one)
-        ts_dev = []
-        s1, dev1 = pipe1.slots[0]["sess"], pipe1.slots[0]["dev_in"]
-        for i in range(3 + 30):
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-            s1.run(dev1)
-            ev1.record()
-            torch.cuda.synchronize()
-            if i >= 3:
-                ts_dev.append(ev0.elapsed_time(ev1))
-        ts_dev.sort()
-        lat = {"p50_ms": p50, "p90_ms": p90, "device_only_p50_ms": ts_dev[len(ts_dev) // 2], "samples": 30,
-               "d2h_bytes": pipe1.last_d2h_bytes,
-               "note": "batch 1, pinned host image in, all outputs back in pinned host memory, wall clock around submit+drain"}
-        pipe1.close()
-        del pipe1
-        pipe_h = HostPipeline(eng, 1, H, W, False, depth=1, out_half=True)
-        lat["p50_ms_half_outputs"] = p50_of(pipe_h, one)[0]
-        pipe_h.close()
-        one_u8 = one.round().clamp(0, 255).to(torch.uint8).pin_memory()
-        pipe_x = HostPipeline(eng, 1, H, W, True, depth=1, extract=True)
-        lat["p50_ms_extracted"] = p50_of(pipe_x, one_u8)[0]
-        pipe_x.close()
-        del pipe_h, pipe_x
-        torch.cuda.empty_cache()
+        lat = measure_latency(eng, full_variants=True)
 
     # ---- per-launch profile (CUDA events on the launch stream) for the roofline of the dominant kernel
     info = sess.op_info()
