@@ -166,3 +166,41 @@ def test_confidence_model_emits_its_extra_heads():
     for k in ref:
         assert torch.equal(got[0][k], ref[k].cpu()), k
     pipe.close()
+
+
+def test_export_and_run_clis_end_to_end(tmp_path):
+    """The reference's two commands, unchanged (export.py:12-41, run.py:11-64): `export.py <cfg> <weights>` writes
+    exported/<cfg>_fp32.pt, `run.py <model.pt> <image>` writes <image>_pred.png; the prediction drawn into the image is
+    what the engine + the reference-identical visualiser produce for that uint8 image."""
+    import os
+    import subprocess
+    import sys
+
+    import cv2
+    import numpy as np
+
+    from densepose_torchscript_b200.config import BUILTIN
+    from densepose_torchscript_b200.engine import Engine
+    from densepose_torchscript_b200.extractor import End2EndVisualizer
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, os.path.join(root, "export.py"), NAME, ""], cwd=tmp_path, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    model = tmp_path / "exported" / (NAME + "_fp32.pt")
+    assert model.exists()
+    img = W.synthetic_image(200, 320, seed=21).round().clamp(0, 255).to(torch.uint8).numpy()
+    src = tmp_path / "frame.png"
+    cv2.imwrite(str(src), img)
+    r = subprocess.run([sys.executable, os.path.join(root, "run.py"), str(model), str(src), "--fp32"], cwd=tmp_path, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = cv2.imread(str(tmp_path / "frame_pred.png"))
+    assert out is not None and out.shape == img.shape
+    eng = Engine(BUILTIN[NAME], W.make_state_dict(O.SPECS[NAME], 0))
+    res = eng.forward_batch(torch.from_numpy(img)[None])[0]
+    want = End2EndVisualizer(alpha=.7, keep_bg=False).visualize(img.copy(), res)
+    assert np.array_equal(out, want)
+    bad = subprocess.run([sys.executable, os.path.join(root, "export.py"), "densepose_rcnn_R_50_FPN_typo", ""], cwd=tmp_path,
+                         env=env, capture_output=True, text=True, timeout=120)
+    assert bad.returncode != 0 and "builtin" in (bad.stderr + bad.stdout)
