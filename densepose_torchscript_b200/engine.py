@@ -256,6 +256,7 @@ class HostPipeline:
       2. batch k is enqueued behind them (H2D copy -> forward -> D2H of boxes / scores / counts);
       3. the copies issued by the PREVIOUS call have had a whole call to finish: they are waited for and returned.
 
+    One pipeline belongs to one host thread (submit / drain are not re-entrant); use one pipeline per thread or GPU.
     Lifetime of returned tensors: they are views of pinned host buffers owned by the pipeline; `depth + 1` result sets
     rotate, so what one submit() returns stays valid until the NEXT submit() has returned, and everything drain()
     returns is valid together. Copy what must live longer.
@@ -320,6 +321,11 @@ class HostPipeline:
         self.slots = []
         self.sets = []
         self._pending = None
+        # hand the pinned result sets (GBs at full capacity) back to the OS instead of leaving them in torch's pinned
+        # cache: a process that opens pipelines of several shapes / dtypes must not accumulate them
+        empty = getattr(torch._C, "_host_emptyCache", None)
+        if empty is not None:
+            empty()
 
     # ---- step 1: the slot's forward is done -> enqueue the (count-aware) copies of its results, do not wait
     def _issue(self, sl) -> Optional[dict]:
