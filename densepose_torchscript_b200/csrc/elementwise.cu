@@ -294,9 +294,52 @@ __device__ __forceinline__ uint4 pack8_f32x2(const uint64_t* acc) {
   return o;
 }
 
-// Both kernels below walk the output in 8x8-pixel tiles (one CTA per tile, one warp per pixel and 16-byte
-// channel chunk per lane when C = 256), so the 5x5 half-resolution pixels a tile samples are fetched from L2
-// once and then hit in L1 instead of being re-read by CTAs that sit a full image row apart.
+// The 2x2 output block (2*by + {0,1}, 2*bx + {0,1}) of a x2 bilinear upsample (align_corners=False) samples the 3x3
+// half-resolution pixels around (by, bx): output 2*by mixes rows (by-1, by) with weights (.25, .75), output 2*by+1 rows
+// (by, by+1) with (.75, .25), the same along x. One thread therefore loads 9 pixels for 4 outputs instead of 16, and
+// unpacks each bf16 pair once; every output is computed by the same lerp4 expression on the same operands as
+// add_up2 (bit-identical results). Interior blocks only (by >= 1, bx >= 1): the first block row / column clamps at
+// the border and goes through add_up2.
+__device__ __forceinline__ void add_up2_block(const uint4* __restrict__ x, int b, int h, int w, int C8, int c, int by,
+                                              int bx, uint64_t (*acc)[4]) {
+  const int r0 = by - 1, r1 = by, r2 = by + 1 < h ? by + 1 : h - 1;
+  const int c0 = bx - 1, c1 = bx, c2 = bx + 1 < w ? bx + 1 : w - 1;
+  const uint4* base = x + (long long)b * h * w * C8 + c;
+  uint4 v[3][3];
+  const int rr[3] = {r0, r1, r2}, cc[3] = {c0, c1, c2};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) v[i][j] = __ldg(base + ((long long)rr[i] * w + cc[j]) * C8);
+  const uint64_t Q = pack_f32x2(__float_as_uint(0.25f), __float_as_uint(0.25f));
+  const uint64_t T = pack_f32x2(__float_as_uint(0.75f), __float_as_uint(0.75f));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint64_t f[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const uint32_t q = k == 0 ? v[i][j].x : k == 1 ? v[i][j].y : k == 2 ? v[i][j].z : v[i][j].w;
+        f[i][j] = bf16x2_to_f32x2(q);
+      }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const uint64_t HY = dy ? T : Q, LY = dy ? Q : T;        // (hy, ly): even row (.25, .75), odd row (.75, .25)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const uint64_t HX = dx ? T : Q, LX = dx ? Q : T;
+        const uint64_t top = fma_f32x2(LX, f[dy][dx + 1], mul_f32x2(HX, f[dy][dx]));
+        const uint64_t bot = fma_f32x2(LX, f[dy + 1][dx + 1], mul_f32x2(HX, f[dy + 1][dx]));
+        acc[dy * 2 + dx][k] = add_f32x2(acc[dy * 2 + dx][k], fma_f32x2(LY, bot, mul_f32x2(HY, top)));
+      }
+    }
+  }
+}
+
+// Both kernels below walk the output in 8x8-pixel tiles (one CTA per tile; a work item is one 2x2 output block x one
+// 16-byte channel chunk), so the 5x5 half-resolution pixels a tile samples are fetched from L2 once and then hit in
+// L1 instead of being re-read by CTAs that sit a full image row apart.
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W, int C8) {
   const int Ho = 2 * H, Wo = 2 * W;
@@ -304,13 +347,20 @@ upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int
   const int b = blockIdx.x / (tiles_x * tiles_y);
   const int t = blockIdx.x - b * tiles_x * tiles_y;
   const int ty0 = (t / tiles_x) * 8, tx0 = (t % tiles_x) * 8;
-  for (int item = threadIdx.x; item < 64 * C8; item += blockDim.x) {
-    const int c = item % C8, pix = item / C8;
-    const int oy = ty0 + (pix >> 3), ox = tx0 + (pix & 7);
-    if (oy >= Ho || ox >= Wo) continue;
-    uint64_t acc[4] = {0, 0, 0, 0};
-    add_up2(x, b, H, W, C8, c, oy, ox, acc);
-    y[(((long long)b * Ho + oy) * Wo + ox) * C8 + c] = pack8_f32x2(acc);
+  for (int item = threadIdx.x; item < 16 * C8; item += blockDim.x) {
+    const int c = item % C8, blk = item / C8;
+    const int by = (ty0 >> 1) + (blk >> 2), bx = (tx0 >> 1) + (blk & 3);
+    if (by >= H || bx >= W) continue;
+    uint64_t acc[4][4] = {};
+    if (by >= 1 && bx >= 1) {
+      add_up2_block(x, b, H, W, C8, c, by, bx, acc);
+    } else {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) add_up2(x, b, H, W, C8, c, 2 * by + (o >> 1), 2 * bx + (o & 1), acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+      y[(((long long)b * Ho + 2 * by + (o >> 1)) * Wo + 2 * bx + (o & 1)) * C8 + c] = pack8_f32x2(acc[o]);
   }
 }
 
@@ -324,25 +374,43 @@ int launch_upsample2x(const bf16* x, bf16* y, int B, int H, int W, int C, cudaSt
   return 0;
 }
 
-__global__ void __launch_bounds__(256)
+#ifndef DPB_MERGE_MINB
+#define DPB_MERGE_MINB 3
+#endif
+__global__ void __launch_bounds__(256, DPB_MERGE_MINB)
 decoder_merge_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b3, const uint4* __restrict__ b4,
                      const uint4* __restrict__ b5, uint4* __restrict__ out, int B, int H, int W, int C8) {
   const int tiles_x = (W + 7) / 8, tiles_y = (H + 7) / 8;
   const int b = blockIdx.x / (tiles_x * tiles_y);
   const int t = blockIdx.x - b * tiles_x * tiles_y;
   const int ty0 = (t / tiles_x) * 8, tx0 = (t % tiles_x) * 8;
-  for (int item = threadIdx.x; item < 64 * C8; item += blockDim.x) {
-    const int c = item % C8, pix = item / C8;
-    const int oy = ty0 + (pix >> 3), ox = tx0 + (pix & 7);
-    if (oy >= H || ox >= W) continue;
-    const long long i = (((long long)b * H + oy) * W + ox) * C8 + c;
-    const uint4 a0 = __ldg(a + i);
-    uint64_t acc[4] = {bf16x2_to_f32x2(a0.x), bf16x2_to_f32x2(a0.y), bf16x2_to_f32x2(a0.z), bf16x2_to_f32x2(a0.w)};
+  const int h = H / 2, w = W / 2;
+  for (int item = threadIdx.x; item < 16 * C8; item += blockDim.x) {
+    const int c = item % C8, blk = item / C8;
+    const int by = (ty0 >> 1) + (blk >> 2), bx = (tx0 >> 1) + (blk & 3);
+    if (by >= h || bx >= w) continue;
+    uint64_t acc[4][4];
+    long long idx[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      idx[o] = (((long long)b * H + 2 * by + (o >> 1)) * W + 2 * bx + (o & 1)) * C8 + c;
+      const uint4 a0 = __ldg(a + idx[o]);
+      acc[o][0] = bf16x2_to_f32x2(a0.x); acc[o][1] = bf16x2_to_f32x2(a0.y);
+      acc[o][2] = bf16x2_to_f32x2(a0.z); acc[o][3] = bf16x2_to_f32x2(a0.w);
+    }
     // reference order: ((p2 + up(p3)) + up(p4)) + up(p5)   (roi_head.py:73-77)
-    add_up2(b3, b, H / 2, W / 2, C8, c, oy, ox, acc);
-    add_up2(b4, b, H / 2, W / 2, C8, c, oy, ox, acc);
-    add_up2(b5, b, H / 2, W / 2, C8, c, oy, ox, acc);
-    out[i] = pack8_f32x2(acc);
+    const uint4* br[3] = {b3, b4, b5};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (by >= 1 && bx >= 1) {
+        add_up2_block(br[j], b, h, w, C8, c, by, bx, acc);
+      } else {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) add_up2(br[j], b, h, w, C8, c, 2 * by + (o >> 1), 2 * bx + (o & 1), acc[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) out[idx[o]] = pack8_f32x2(acc[o]);
   }
 }
 

@@ -306,6 +306,50 @@ def test_upsample_and_decoder_merge(ops):
     assert frac_equal(got, ref) > 0.98 and rel_l2(got, ref) < 3e-3
 
 
+def _up2_exact(x):
+    """The kernels' x2 bilinear arithmetic, emulated exactly: top = fma(lx, q01, hx*q00), bot likewise, out =
+    fma(ly, bot, hy*top) in fp32. With bf16 inputs and weights in {0, .25, .75, 1} every product has <= 10 significant
+    bits and every fp32 rounding can be reproduced by rounding the float64 value."""
+    n, c, h, w = x.shape
+    xd = x.double()
+
+    def taps(size):
+        d = torch.arange(2 * size, dtype=torch.float64)
+        real = (0.5 * (d + 0.5) - 0.5).clamp(min=0)
+        i0 = real.floor().long()
+        i1 = torch.where(i0 < size - 1, i0 + 1, i0)
+        l = real - i0
+        return i0, i1, l
+
+    y0, y1, ly = taps(h)
+    x0, x1, lx = taps(w)
+    f32 = lambda t: t.float().double()                                   # noqa: E731  one fp32 rounding
+    hx, hy = 1 - lx, 1 - ly
+    q00, q01 = xd[:, :, y0][:, :, :, x0], xd[:, :, y0][:, :, :, x1]
+    q10, q11 = xd[:, :, y1][:, :, :, x0], xd[:, :, y1][:, :, :, x1]
+    top = f32(lx * q01 + f32(hx * q00))
+    bot = f32(lx * q11 + f32(hx * q10))
+    return f32(ly[:, None] * bot + f32(hy[:, None] * top))
+
+
+def test_upsample_and_decoder_merge_exact_arithmetic(ops):
+    """The 2x2-block kernels (9 loads per 4 outputs) must give, bit for bit, the per-output expression above: upsample =
+    bf16(0 + lerp), merge = bf16(((a + up(b3)) + up(b4)) + up(b5)) with fp32 adds (roi_head.py:73-77)."""
+    g = torch.Generator().manual_seed(7)
+    for (h, w) in ((13, 21), (1, 5), (4, 1), (25, 42)):
+        x = bf16(torch.randn(2, 256, h, w, generator=g))
+        want = _up2_exact(x).float().to(torch.bfloat16)
+        got = ops.upsample2x(nhwc_bf16_cuda(x)).permute(0, 3, 1, 2).cpu()
+        assert torch.equal(got, want), (h, w)
+    a = bf16(torch.randn(2, 256, 26, 42, generator=g))
+    bs = [bf16(torch.randn(2, 256, 13, 21, generator=g)) for _ in range(3)]
+    acc = a.double()
+    for t in bs:
+        acc = (acc + _up2_exact(t)).float().double()
+    got = ops.decoder_merge(nhwc_bf16_cuda(a), *[nhwc_bf16_cuda(t) for t in bs]).permute(0, 3, 1, 2).cpu()
+    assert torch.equal(got, acc.float().to(torch.bfloat16))
+
+
 # ----------------------------------------------------------------------------------------------- RPN
 def _rpn_inputs(seed, sizes, quant=None):
     g = torch.Generator().manual_seed(seed)
