@@ -77,10 +77,16 @@ __global__ void __launch_bounds__(256) roi_align_kernel(RoiAlignArgs a, float on
     lvl = (int)l - 2;
     if (lvl >= a.n_levels) lvl = a.n_levels - 1;
   }
-  const int H = a.H[lvl], W = a.W[lvl];
-  const float scale = a.scale[lvl];
+  // per-level parameters picked with constant indices: indexing the by-value argument struct with a run-time
+  // `lvl` would make every thread copy its arrays to local memory (a 128-byte stack frame in round 1)
+  int H = a.H[0], W = a.W[0];
+  float scale = a.scale[0];
+  const bf16* fbase = a.feat[0];
+#pragma unroll
+  for (int l = 1; l < 4; ++l)
+    if (lvl == l) { H = a.H[l]; W = a.W[l]; scale = a.scale[l]; fbase = a.feat[l]; }
   const int C8 = a.C / 8;
-  const uint4* feat = reinterpret_cast<const uint4*>(a.feat[lvl]) + (long long)b * H * W * C8;
+  const uint4* feat = reinterpret_cast<const uint4*>(fbase) + (long long)b * H * W * C8;
   const int P = a.P;
   {
     const float fx0 = __fmul_rn(x1, scale), fy0 = __fmul_rn(y1, scale);

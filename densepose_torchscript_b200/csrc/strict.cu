@@ -205,11 +205,16 @@ __global__ void __launch_bounds__(256) roi_align_split_kernel(RoiAlignArgs a, Ro
     lvl = (int)l - 2;
     if (lvl >= a.n_levels) lvl = a.n_levels - 1;
   }
-  const int H = a.H[lvl], W = a.W[lvl];
-  const float scale = a.scale[lvl];
+  int H = a.H[0], W = a.W[0];                 // constant-index selection: no local-memory copy of the argument structs
+  float scale = a.scale[0];
+  const bf16* fbase = a.feat[0];
+  const bf16* fbase_lo = sp.feat_lo[0];
+#pragma unroll
+  for (int l = 1; l < 4; ++l)
+    if (lvl == l) { H = a.H[l]; W = a.W[l]; scale = a.scale[l]; fbase = a.feat[l]; fbase_lo = sp.feat_lo[l]; }
   const int C8 = a.C / 8;
-  const uint4* fh = reinterpret_cast<const uint4*>(a.feat[lvl]) + (long long)b * H * W * C8;
-  const uint4* fl = reinterpret_cast<const uint4*>(sp.feat_lo[lvl]) + (long long)b * H * W * C8;
+  const uint4* fh = reinterpret_cast<const uint4*>(fbase) + (long long)b * H * W * C8;
+  const uint4* fl = reinterpret_cast<const uint4*>(fbase_lo) + (long long)b * H * W * C8;
   const int P = a.P;
   {
     const float fx0 = __fmul_rn(x1, scale), fy0 = __fmul_rn(y1, scale);
