@@ -112,7 +112,11 @@ __global__ void __launch_bounds__(256) roi_align_kernel(RoiAlignArgs a, float on
   const int group = threadIdx.x / C8, groups = blockDim.x / C8;
   const uint4* fc = feat + chunk;
   const uint64_t one = pack_f32x2(__float_as_uint(one_f), __float_as_uint(one_f));
-  for (int bin = group; bin < P * P; bin += groups) {
+  // gridDim.y CTAs share one ROI (contiguous slices of its bins): with one CTA per ROI the 800 DensePose ROIs of a
+  // batch are 1.35 waves of the 592 resident CTAs, i.e. the second wave runs at a third of the machine
+  const int per = (P * P + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int bin_end = min(P * P, ((int)blockIdx.y + 1) * per);
+  for (int bin = (int)blockIdx.y * per + group; bin < bin_end; bin += groups) {
     const int ph = bin / P, pw = bin - ph * P;
     uint64_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;    // four (+0, +0) pairs = 8 channels
 #pragma unroll
@@ -156,7 +160,8 @@ int launch_roi_align(const RoiAlignArgs& a, cudaStream_t s) {
   if (a.C % 8 || 256 % (a.C / 8)) { set_error("roi_align: C/8 must divide 256"); return -1; }
   if (a.P > 32) { set_error("roi_align: pooler resolution %d > 32", a.P); return -1; }
   if (a.R == 0) return 0;
-  roi_align_kernel<<<a.R, 256, 0, s>>>(a, 1.0f);   // 1.0f as a run-time value: see tap_accum
+  const int parts = a.P >= 14 ? 4 : 1;             // large poolers: several CTAs per ROI (wave quantisation)
+  roi_align_kernel<<<dim3(a.R, parts), 256, 0, s>>>(a, 1.0f);   // 1.0f as a run-time value: see tap_accum
   DPB_CHECK_LAUNCH("roi_align");
   return 0;
 }
