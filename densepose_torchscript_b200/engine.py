@@ -288,6 +288,11 @@ class HostPipeline:
                 self.slots.append(dict(sess=sess, dev_in=dev_in, host_in=host_in, small_dev=small_dev,
                                        small_host=small_host, done=torch.cuda.Event(), busy=False,
                                        ex_dev=[None, None], ex_host=[None, None], ex_flip=0))
+                if extract:
+                    # both extraction buffer sets of the slot exist before the first batch: a pinned allocation
+                    # (cudaHostAlloc, milliseconds) never lands inside a serving loop unless a batch outgrows them
+                    for flip in (0, 1):
+                        self._ex_buffers(self.slots[-1], flip, 0)
             # depth + 1 rotating result sets for the big tensors (full capacity, pinned): up to depth batches in the
             # slots plus one whose copy has been issued can be in flight, and a returned set is not refilled before the
             # next submit() has returned
@@ -351,6 +356,19 @@ class HostPipeline:
         ticket["event"].record(sess.stream)
         return ticket
 
+    def _ex_buffers(self, sl, flip: int, total: int):
+        """Device + pinned host buffers of one extraction (labels, uv) holding at least `total` pixels."""
+        ex_dev, ex_host = sl["ex_dev"][flip], sl["ex_host"][flip]
+        if ex_dev is None or ex_dev[0].numel() < total:
+            dev = self.engine.device
+            lab_dt = torch.uint8 if self.labels_u8 else torch.int64
+            cap = max(int(total * 1.25), 1 << 20)
+            with torch.cuda.device(dev):
+                ex_dev = (torch.empty(cap, dtype=lab_dt, device=dev), torch.empty(2 * cap, dtype=torch.float32, device=dev))
+            ex_host = (torch.empty(cap, dtype=lab_dt).pin_memory(), torch.empty(2 * cap, dtype=torch.float32).pin_memory())
+            sl["ex_dev"][flip], sl["ex_host"][flip] = ex_dev, ex_host
+        return ex_dev, ex_host
+
     def _issue_extraction(self, sl, ticket):
         from . import ops
         sess, boxes, counts = ticket["sess"], ticket["boxes"], ticket["counts"]
@@ -360,17 +378,10 @@ class HostPipeline:
         packed = torch.cat([boxes[b, :cnt[b]] for b in range(sess.batch)]) if sum(cnt) else boxes.new_zeros((0, 4))
         boxes_xywh, wh, offsets = ops.box_sizes(packed)
         total = int(offsets[-1])
-        lab_dt = torch.uint8 if self.labels_u8 else torch.int64
         lab_b = 1 if self.labels_u8 else 8
         flip = sl["ex_flip"]                               # two buffer sets per slot: what was returned stays intact
         sl["ex_flip"] ^= 1
-        ex_dev, ex_host = sl["ex_dev"][flip], sl["ex_host"][flip]
-        if ex_dev is None or ex_dev[0].numel() < total:
-            cap = max(int(total * 1.25), 1 << 20)
-            with torch.cuda.device(dev):
-                ex_dev = (torch.empty(cap, dtype=lab_dt, device=dev), torch.empty(2 * cap, dtype=torch.float32, device=dev))
-            ex_host = (torch.empty(cap, dtype=lab_dt).pin_memory(), torch.empty(2 * cap, dtype=torch.float32).pin_memory())
-            sl["ex_dev"][flip], sl["ex_host"][flip] = ex_dev, ex_host
+        ex_dev, ex_host = self._ex_buffers(sl, flip, total)
         n = int(sum(cnt))
         if n and total:
             with torch.cuda.device(dev), torch.cuda.stream(sess.stream):
