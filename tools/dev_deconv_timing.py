@@ -34,6 +34,8 @@ def main():
     out = torch.empty(R, 4 * Cp, P, P, device="cuda")
     flops = 2.0 * R * P * P * 4 * Cp * 4 * Cin
     ref = None
+    ms = ev_time(lambda: ops.conv2d(x, packed, bias, 2, 2, pad=1, planar=True, out=out, phase_taps=True, pair=1, tiled=True))
+    print(f"tiled A loads (28 x 4 pixel boxes, 112-row tiles): {ms:.4f} ms")
     for pair in (1, 2):
         for stages in (0, 3, 4, 5, 6):
             for ks in (0, 1, 2):
