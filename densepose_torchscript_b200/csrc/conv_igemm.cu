@@ -744,6 +744,21 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
         if (d.cout_pad % b == 0) { block_n = b; break; }
     }
   }
+  if (d.block_n == 0 && !d.phase_taps) {
+    // Few-tile launches (batch 1: res4 / res5 / FPN p5 / FC1 have 8-33 row tiles): a 256-wide N tile leaves most SMs
+    // idle while each busy one walks the whole K loop at 512 cycles per chunk. Narrower N tiles put 2-4x the CTAs to
+    // work and a 64-wide tile's chunk costs ~330 cycles (its A load), so the launch's critical path shrinks by up to a
+    // half; the extra A traffic is free while the machine is not full. Results do not depend on the N tile.
+    long long m_tiles;
+    if (d.im2col) {
+      m_tiles = ((long long)d.N * d.H_out * d.W_out + 127) / 128;
+    } else {
+      int tw, th, tn;
+      choose_tile(d.W_out, d.H_out, d.N, d.sx, d.sy, &tw, &th, &tn);
+      m_tiles = (long long)ceil_div(d.W_out, tw) * ceil_div(d.H_out, th) * ceil_div(d.N, tn);
+    }
+    while (block_n >= 128 && (block_n / 2) % 64 == 0 && m_tiles * (d.cout_pad / block_n) * 2 <= num_sms) block_n /= 2;
+  }
   if (d.phase_taps) {
     if (d.cout_pad % 64 != 0 || d.kh != 2 || d.kw != 2 || d.pad_x != 1 || d.pad_y != 1 || d.sx != 1 || d.sy != 1) {
       set_error("conv: phase_taps needs k=2, pad=1, stride 1 and cout_pad = 4 x (multiple of 16)");

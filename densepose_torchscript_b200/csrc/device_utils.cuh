@@ -71,6 +71,19 @@ __device__ __forceinline__ uint32_t cluster_map_shared(uint32_t saddr, uint32_t 
 __device__ __forceinline__ void st_shared_cluster_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_shared_cluster_u64(uint32_t addr, unsigned long long v) {
+  asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_cluster_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t atom_add_shared_cluster_u32(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared::cluster.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ double ld_shared_cluster_f64(uint32_t addr) {
   double v;
   asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
@@ -158,23 +171,27 @@ static __device__ bool nms_sorted_block(const float4* __restrict__ g_boxes, int 
       uint32_t rw = __shfl_sync(0xffffffffu, removed, w);          // warp-uniform
       const int row = w * 32 + lane;
       const uint32_t diag = (row < n) ? mask[row * 32 + w] : 0u;    // suppression inside this word (bits j > i)
-      uint32_t d[32];
+      // word `lane` of the 32 rows of this block, loaded before the scan needs them: the loads do not depend on
+      // which boxes survive, so their latency hides behind the serial chain below (words left of the diagonal
+      // are never written: those lanes load nothing)
+      const bool later = lane > w && lane < nw;
+      uint32_t r[32];
 #pragma unroll
-      for (int b = 0; b < 32; ++b) d[b] = __shfl_sync(0xffffffffu, diag, b);
-      uint32_t kw = 0;
+      for (int b = 0; b < 32; ++b) r[b] = later ? mask[(w * 32 + b) * 32 + lane] : 0u;
+      // greedy order inside the word: box b survives iff its bit is still clear when its turn comes; a row only
+      // has bits j > b, so bit b is final after step b and the kept set is the complement of the final word.
+      // Two dependent ALU operations per step (test, predicated OR).
 #pragma unroll
       for (int b = 0; b < 32; ++b) {
-        const uint32_t alive = ((rw >> b) & 1u) ^ 1u;
-        kw |= alive << b;
-        rw |= d[b] & (0u - alive);
+        const uint32_t db = __shfl_sync(0xffffffffu, diag, b);
+        if (!(rw & (1u << b))) rw |= db;
       }
+      const uint32_t kw = ~rw;
       if (lane == w) kept = kw;
-      // rows of the kept boxes suppress later words (words left of the diagonal are never written)
+      // rows of the kept boxes suppress later words
       uint32_t acc = 0;
-      for (uint32_t m = kw; m != 0; m &= m - 1) {
-        const int bsel = __ffs((int)m) - 1;
-        if (lane > w && lane < nw) acc |= mask[(w * 32 + bsel) * 32 + lane];
-      }
+#pragma unroll
+      for (int b = 0; b < 32; ++b) acc |= (kw >> b) & 1u ? r[b] : 0u;
       removed |= acc;
     }
     alive_words[lane] = kept;

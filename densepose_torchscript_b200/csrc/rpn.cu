@@ -45,9 +45,15 @@ __device__ __forceinline__ void decode_box(const float* __restrict__ d, float ax
   out[3] = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
 }
 
+// A cluster of nc CTAs per (level, image): a p2 level is 1.6 M logits that one CTA would stream four times (three
+// histogram passes and the collection); here every CTA takes a contiguous slice of the pixels, the per-pass
+// histograms stay in each CTA's shared memory and every CTA sums them through distributed shared memory (so all of
+// them walk the same radix path without a broadcast), and the selected keys are appended to CTA 0's list with
+// cluster-scope atomics. CTA 0 sorts, decodes and writes.
 __global__ void __launch_bounds__(1024)
-rpn_topk_decode_kernel(RpnArgs a) {
-  const int lvl = blockIdx.x, b = blockIdx.y;
+rpn_topk_decode_kernel(RpnArgs a, int nc) {
+  const int lvl = blockIdx.x / nc, b = blockIdx.y;
+  const uint32_t rank = nc > 1 ? cluster_ctarank() : 0u;
   const RpnLevel& L = a.lvl[lvl];
   const int n = L.H * L.W * 3;
   const int k = n < a.pre_topk ? n : a.pre_topk;
@@ -61,39 +67,55 @@ rpn_topk_decode_kernel(RpnArgs a) {
   const int npix = L.H * L.W;
   const float4* head4 = reinterpret_cast<const float4*>(head);
   auto key_at = [&](int i) -> uint32_t { return f2ord(__ldg(head + (long long)(i / 3) * 16 + (i % 3))); };
+  // this CTA's pixels
+  const int per = (npix + nc - 1) / nc;
+  const int px_lo = (int)rank * per, px_hi = min(npix, px_lo + per);
+  const uint32_t hist_sa = (uint32_t)__cvta_generic_to_shared(hist);
+  // merged count of one bin: the sum over the cluster's histograms
+  auto merged = [&](int bin) -> unsigned {
+    if (nc == 1) return hist[bin];
+    unsigned c = 0;
+    for (int r = 0; r < nc; ++r) c += ld_shared_cluster_u32(cluster_map_shared(hist_sa + 4u * (uint32_t)bin, (uint32_t)r));
+    return c;
+  };
+
+  if (threadIdx.x == 0) { s_cnt = 0; s_eq_taken = 0; }
+  keys[threadIdx.x] = 0ull;
 
   uint32_t prefix = 0, mask = 0;
   unsigned remaining = (unsigned)k;
+  unsigned eq_total = 0;
   const int shifts[3] = {21, 10, 0};
   const int bits[3] = {11, 11, 10};
   for (int pass = 0; pass < 3; ++pass) {
     const int nb = 1 << bits[pass];
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    // one CTA streams a whole level (1 MB for p2): four independent 16-byte loads per thread are issued before any
-    // is used, otherwise every pass is a chain of dependent L2 round trips
-    for (int px0 = threadIdx.x; px0 < npix; px0 += 4 * blockDim.x) {
+    // four independent 16-byte loads per thread are issued before any is used, otherwise every pass is a chain of
+    // dependent L2 round trips
+    for (int px0 = px_lo + threadIdx.x; px0 < px_hi; px0 += 4 * blockDim.x) {
       float4 v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int px = px0 + j * blockDim.x;
-        if (px < npix) v[j] = __ldg(head4 + (long long)px * 4);   // (logit a0, a1, a2, first delta): one 16-byte load
+        if (px < px_hi) v[j] = __ldg(head4 + (long long)px * 4);   // (logit a0, a1, a2, first delta): one 16-byte load
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (px0 + j * (int)blockDim.x >= npix) break;
+        if (px0 + j * (int)blockDim.x >= px_hi) break;
         const uint32_t u0 = f2ord(v[j].x), u1 = f2ord(v[j].y), u2 = f2ord(v[j].z);
         if ((u0 & mask) == prefix) atomicAdd(&hist[(u0 >> shifts[pass]) & (nb - 1)], 1u);
         if ((u1 & mask) == prefix) atomicAdd(&hist[(u1 >> shifts[pass]) & (nb - 1)], 1u);
         if ((u2 & mask) == prefix) atomicAdd(&hist[(u2 >> shifts[pass]) & (nb - 1)], 1u);
       }
     }
-    __syncthreads();
+    if (nc > 1) cluster_sync_all();          // every CTA's histogram is complete and visible
+    else __syncthreads();
     // reversed bins: thread t owns reversed positions 2t, 2t+1 (bin = nb-1-pos)
     unsigned c0 = 0, c1 = 0;
     const int p0 = 2 * threadIdx.x, p1 = p0 + 1;
-    if (p0 < nb) c0 = hist[nb - 1 - p0];
-    if (p1 < nb) c1 = hist[nb - 1 - p1];
+    if (p0 < nb) c0 = merged(nb - 1 - p0);
+    if (p1 < nb) c1 = merged(nb - 1 - p1);
     const unsigned incl = block_scan_incl(c0 + c1, warp_sums);
     const unsigned before = incl - (c0 + c1);
     if (before < remaining && remaining <= incl) {
@@ -104,40 +126,52 @@ rpn_topk_decode_kernel(RpnArgs a) {
     prefix |= (s_bin << shifts[pass]);
     mask |= ((uint32_t)(nb - 1) << shifts[pass]);
     remaining -= s_above;
-    __syncthreads();
+    if (pass == 2) eq_total = merged((int)s_bin);       // elements equal to the k-th key
+    if (nc > 1) cluster_sync_all();          // all remote reads of this pass are done before any histogram is reset
+    else __syncthreads();
   }
   // prefix == k-th largest key T; `remaining` of the elements equal to T are needed.
   const uint32_t T = prefix;
-  const unsigned eq_total = hist[T & 1023u];
-  if (threadIdx.x == 0) { s_cnt = 0; s_eq_taken = 0; }
-  keys[threadIdx.x] = 0ull;
-  __syncthreads();
   const bool take_all_eq = (eq_total == remaining);
-  for (int px0 = threadIdx.x; px0 < npix; px0 += 4 * blockDim.x) {
+  const uint32_t cnt_sa = cluster_map_shared((uint32_t)__cvta_generic_to_shared(&s_cnt), 0u);
+  const uint32_t keys_sa = cluster_map_shared((uint32_t)__cvta_generic_to_shared(keys), 0u);
+  for (int px0 = px_lo + threadIdx.x; px0 < px_hi; px0 += 4 * blockDim.x) {
     float4 v4[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int px = px0 + j * blockDim.x;
-      if (px < npix) v4[j] = __ldg(head4 + (long long)px * 4);
+      if (px < px_hi) v4[j] = __ldg(head4 + (long long)px * 4);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int px = px0 + j * blockDim.x;
-      if (px >= npix) break;
+      if (px >= px_hi) break;
       const uint32_t us[3] = {f2ord(v4[j].x), f2ord(v4[j].y), f2ord(v4[j].z)};
 #pragma unroll
       for (int an = 0; an < 3; ++an) {
         const uint32_t u = us[an];
         if (u > T || (take_all_eq && u == T)) {
-          const unsigned pos = atomicAdd(&s_cnt, 1u);
-          if (pos < 1024) keys[pos] = ((unsigned long long)u << 32) | (0xFFFFFFFFu - (uint32_t)(px * 3 + an));
+          // the list lives in CTA 0 (its order does not matter: it is sorted by (score, ~index) below)
+          const unsigned long long key = ((unsigned long long)u << 32) | (0xFFFFFFFFu - (uint32_t)(px * 3 + an));
+          if (nc > 1) {
+            const unsigned pos = atom_add_shared_cluster_u32(cnt_sa, 1u);
+            if (pos < 1024) st_shared_cluster_u64(keys_sa + 8u * pos, key);
+          } else {
+            const unsigned pos = atomicAdd(&s_cnt, 1u);
+            if (pos < 1024) keys[pos] = key;
+          }
         }
       }
     }
   }
-  __syncthreads();
+  if (nc > 1) {
+    cluster_sync_all();                      // every key has landed in CTA 0
+    if (rank != 0) return;
+  } else {
+    __syncthreads();
+  }
   if (!take_all_eq) {
-    // excess ties: keep the lowest-index ones, chunk by chunk in index order
+    // excess ties: keep the lowest-index ones, chunk by chunk in index order (CTA 0 walks the whole level: rare)
     for (int base = 0; base < n; base += blockDim.x) {
       const int i = base + threadIdx.x;
       const unsigned flag = (i < n && key_at(i) == T) ? 1u : 0u;
@@ -187,14 +221,6 @@ rpn_topk_decode_kernel(RpnArgs a) {
     a.cand_keep[slot] = 0;
   }
   if (t == 0) a.cand_count[b * 5 + lvl] = k;
-}
-
-int launch_rpn_topk_decode(const RpnArgs& a, cudaStream_t s) {
-  if (a.pre_topk > 1024) { set_error("rpn: pre_topk > 1024 unsupported"); return -1; }
-  dim3 grid(5, a.B);
-  rpn_topk_decode_kernel<<<grid, 1024, 0, s>>>(a);
-  DPB_CHECK_LAUNCH("rpn_topk_decode");
-  return 0;
 }
 
 static constexpr int kNmsSmem = 1024 * 32 * 4 + 1024 * 16 + 1024 * 4 + 32 * 4;
@@ -248,6 +274,14 @@ static cudaError_t launch_clustered(void (*fn)(KArgs...), dim3 grid, int threads
   attr[0].val.clusterDim.x = nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, fn, args...);
+}
+
+int launch_rpn_topk_decode(const RpnArgs& a, cudaStream_t s) {
+  if (a.pre_topk > 1024) { set_error("rpn: pre_topk > 1024 unsupported"); return -1; }
+  const int nc = pick_nms_cluster(5 * a.B, device_sms());
+  cudaError_t e = launch_clustered(rpn_topk_decode_kernel, dim3(5 * nc, a.B), 1024, 0, nc, s, a, nc);
+  if (e != cudaSuccess) { set_error("rpn_topk_decode launch: %s", cudaGetErrorString(e)); return -4; }
+  return 0;
 }
 
 int launch_rpn_nms(const RpnArgs& a, cudaStream_t s) {
