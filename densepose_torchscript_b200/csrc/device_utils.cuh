@@ -89,6 +89,13 @@ __device__ __forceinline__ double ld_shared_cluster_f64(uint32_t addr) {
   asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
   return v;
 }
+// the two halves of a cluster barrier (every thread of every CTA executes both, in this order)
+__device__ __forceinline__ void cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // all threads of all CTAs of the cluster; release/acquire orders shared::cluster and global accesses
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -113,6 +120,9 @@ static __device__ bool nms_sorted_block(const float4* __restrict__ g_boxes, int 
   float* areas = reinterpret_cast<float*>(boxes + 1024);
   uint32_t* alive_words = reinterpret_cast<uint32_t*>(areas + 1024);   // 32
   const uint32_t rank = NC > 1 ? cluster_ctarank() : 0u;
+  // distributed shared memory of a CTA may only be touched once that CTA runs: arrive now, wait just before the first
+  // remote store of the mask phase (the box loads in between hide the barrier)
+  if (NC > 1) cluster_arrive();
   if (threadIdx.x < 32) alive_words[threadIdx.x] = 0;
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -122,6 +132,7 @@ static __device__ bool nms_sorted_block(const float4* __restrict__ g_boxes, int 
     if (keep_io[i]) atomicOr(&alive_words[i >> 5], 1u << (i & 31));
   }
   __syncthreads();
+  if (NC > 1) cluster_wait();
   const int nw = (n + 31) >> 5;
   {
     // lane = column, the word is a ballot. Box reads are conflict-free (consecutive float4 per lane, row box

@@ -212,6 +212,26 @@ def test_conv_strict_mode_is_fp32_class(ops, case):
     assert float((got - ref).norm() / ref.norm()) < (2e-5 if Cin * k * k <= 4608 else 1e-4)
 
 
+@pytest.mark.parametrize("case", [(1, 25, 42, 512, 512, 3, 1), (1, 50, 84, 1024, 256, 1, 0), (1, 50, 84, 256, 1024, 1, 0),
+                                  (1000, 1, 1, 12544, 1024, 1, 0)])
+def test_conv_result_does_not_depend_on_the_n_tile(ops, case):
+    """Few-tile launches (batch 1) pick a narrower N tile so that more SMs work (conv_plan_build); the K order of every
+    output element is unchanged, so the automatic plan must equal the forced 256- and 64-wide ones bit for bit."""
+    N, H, W, Cin, Cout, k, pad = case
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(N, H, W, Cin, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
+    packed, bias, _, _ = ops.pack_conv_weight(w, torch.randn(Cout, generator=g))
+    packed, bias = packed.cuda(), bias.cuda()
+    res = (torch.randn(N, H, W, Cout, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    outs = [ops.conv2d(x, packed, bias, k, k, 1, pad, 1, True, res=res, block_n=bn) for bn in (0, 256, 64)]
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2).cpu(), bf16(w), bias.cpu(), padding=pad).permute(0, 2, 3, 1) + res.float().cpu()
+    err = (outs[0].float().cpu() - ref.clamp_min(0)).abs().max()
+    assert float(err) <= float(ref.abs().max()) * 2.0 ** -7
+
+
 def test_conv_fp32_out_and_n_valid(ops):
     g = torch.Generator().manual_seed(5)
     x = bf16(torch.randn(9, 256, 28, 28, generator=g))
@@ -393,6 +413,27 @@ def test_rpn_proposals_match_oracle(ops):
     assert torch.equal(scores[0, :n].cpu(), ref["objectness_logits"])   # NMS keep set + merged order: exact
     assert torch.allclose(boxes[0, :n].cpu(), ref["proposal_boxes"], rtol=1e-5, atol=1e-3)
     assert float(boxes[0, :n, 0::2].max()) <= Hp and float(boxes[0, :n, 1::2].max()) <= Wp
+
+
+@pytest.mark.parametrize("batch", [2, 4, 5, 6, 10, 16])
+def test_rpn_proposals_batched_every_cluster_size(ops, batch):
+    """The top-k and the NMS run as clusters of 8 / 7 / 5 / 4 / 2 / 1 CTAs per (level, image) depending on the batch
+    (pick_nms_cluster); a batch is B independent images: every image must give what it gives alone (batch 1 = clusters
+    of 8, pinned against the oracle above), bit for bit, including heavy ties in one of them."""
+    sizes = [(64, 96), (32, 48), (16, 24), (8, 12), (4, 6)]
+    per_image = [_rpn_inputs(100 + i, sizes, quant=0.5 if i == 1 else None)[2] for i in range(batch)]
+    heads = [torch.cat([per_image[i][l] for i in range(batch)]).contiguous() for l in range(5)]
+    boxes, scores, counts, dbg = ops.rpn_proposals(heads, clip_x=256.0, clip_y=384.0)
+    torch.cuda.synchronize()
+    for i in range(batch):
+        b1, s1, c1, d1 = ops.rpn_proposals(per_image[i], clip_x=256.0, clip_y=384.0)
+        torch.cuda.synchronize()
+        n = int(c1[0])
+        assert int(counts[i]) == n
+        assert torch.equal(scores[i, :n], s1[0, :n]) and torch.equal(boxes[i, :n], b1[0, :n])
+        assert torch.equal(dbg["cand_count"][i], d1["cand_count"][0])
+        assert torch.equal(dbg["cand_scores"][i], d1["cand_scores"][0])
+        assert torch.equal(dbg["cand_keep"][i], d1["cand_keep"][0])
 
 
 def test_rpn_topk_with_many_ties(ops):
