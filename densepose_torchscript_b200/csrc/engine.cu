@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <functional>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -47,6 +48,14 @@ struct dpb200_session {
   std::vector<double> op_flops;          // padded-shape 2*MAC at full capacity (conv ops), else 0
   std::vector<double> op_bytes;          // algorithmic HBM bytes at full capacity: every operand read once, outputs written once
   std::vector<ConvPlan*> plans;
+  // Execution schedule: the launches of `ops` on two streams (0 = the caller's, 1 = a side stream owned by the session)
+  // with explicit event edges, i.e. a two-branch graph once captured. Every event is recorded (in enqueue order) before
+  // anything waits for it; the last item joins the side stream back.
+  struct Sched { unsigned char kind, stream; short idx; };   // kind 0: launch ops[idx]; 1: record event idx; 2: wait for event idx
+  std::vector<Sched> sched;
+  cudaStream_t side = nullptr;
+  static constexpr int kEvents = 12;
+  cudaEvent_t evs[kEvents] = {};
   std::map<std::string, TensorInfo> taps;
   double flops = 0;
   // run-time bound pointers
@@ -63,6 +72,8 @@ struct dpb200_session {
   dpb200_forward_io graph_io{};
   ~dpb200_session() {
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    for (auto e : evs) if (e) cudaEventDestroy(e);
+    if (side) cudaStreamDestroy(side);
     for (auto* p : plans) delete p;
   }
 };
@@ -75,6 +86,9 @@ struct Builder {
   dpb200_session* s;
   const dpb200_model* m;
   int fail = 0;
+  unsigned char stream = 0;      // stream of the launches being recorded (dpb200_session::sched)
+  void record(int ev) { if (!fail) s->sched.push_back({1, stream, (short)ev}); }
+  void wait(int ev) { if (!fail) s->sched.push_back({2, stream, (short)ev}); }
 
   void* alloc(size_t bytes) {
     size_t off = (s->ws_used + 1023) & ~(size_t)1023;
@@ -162,6 +176,7 @@ struct Builder {
     const double fl = 2.0 * x.N * d.H_out * d.W_out * (double)w->cout_pad * d.kh * d.kw * w->cin_pad * (strict() ? 3 : 1);
     s->flops += fl;
     s->op_names.push_back("conv:" + wname);
+    s->sched.push_back({0, stream, (short)s->ops.size()});
     s->op_flops.push_back(fl);
     {
       // input pixels a 1x1 strided conv never touches are not counted; weights and bias once
@@ -182,6 +197,7 @@ struct Builder {
   void op(std::function<int(cudaStream_t)> f, const char* name = "stage", double bytes = 0.0) {
     if (fail) return;
     s->op_names.push_back(name);
+    s->sched.push_back({0, stream, (short)s->ops.size()});
     s->op_flops.push_back(0.0);
     s->op_bytes.push_back(bytes);
     if (s->dry) { s->ops.push_back([](cudaStream_t) { return 0; }); return; }
@@ -298,33 +314,25 @@ int build_plan(dpb200_session* s) {
     b.tap("res" + std::to_string(si + 2), cur);
   }
 
-  // ---- a5 FPN
+  // ---- a5 FPN + a7 RPN head, on two streams: the top-down lateral chain, the p2-sized convs (output2, the RPN head on
+  // p2) stay on the caller's stream; the small 3x3 output convs of p5 / p4 / p3 and the RPN head on p3..p6 (a handful of
+  // row tiles each, latency-bound) run on the side stream as soon as their lateral map exists.
+  enum { EV_LAT5 = 0, EV_LAT4, EV_LAT3, EV_SIDE_FPN, EV_MAIN_RPN, EV_CHAIN };
   T4 lat[4], pf[5];
-  for (int l = 3; l >= 0; --l) {
-    lat[l] = b.act(B, res_out[l].H, res_out[l].W, 256);
-    Builder::ConvOpt o; o.k = 1;
-    if (l < 3) { o.res = &lat[l + 1]; o.res_shift = 1; }
-    b.conv("backbone.fpn_lateral" + std::to_string(l + 2), res_out[l], lat[l], o);
-    pf[l] = b.act(B, res_out[l].H, res_out[l].W, 256);
-    Builder::ConvOpt oo; oo.k = 3; oo.pad = 1;
-    b.conv("backbone.fpn_output" + std::to_string(l + 2), lat[l], pf[l], oo);
-    b.tap("p" + std::to_string(l + 2), pf[l]);
-  }
-  // p6 = p5[:, ::2, ::2] (LastLevelMaxPool, fpn.py:199) is only ever read by the RPN conv: strided view.
-  const int H6 = (pf[3].H + 1) / 2, W6 = (pf[3].W + 1) / 2;
-
-  // ---- a7 RPN head
-  T4 rpn_t = b.act(B, pf[0].H, pf[0].W, 256);
   RpnArgs ra{};
   T4 rpn_head[5];
-  for (int l = 0; l < 5; ++l) {
+  // p6 = p5[:, ::2, ::2] (LastLevelMaxPool, fpn.py:199) is only ever read by the RPN conv: strided view.
+  const int H6 = (res_out[3].H + 1) / 2, W6 = (res_out[3].W + 1) / 2;
+  T4 rpn_t = b.act(B, res_out[0].H, res_out[0].W, 256);          // RPN hidden map: p2 on the main stream ...
+  T4 rpn_t_side = b.act(B, res_out[1].H, res_out[1].W, 256);     // ... p3..p6 on the side stream (one after the other)
+  auto rpn_level = [&](int l, const T4& scratch) {
     T4 xin = l < 4 ? pf[l] : pf[3];
     Builder::ConvOpt o; o.k = 3; o.pad = 1; o.relu = 1;
     if (l == 4) {
       xin.H = H6; xin.W = W6;
       o.x_sw = 2 * 256; o.x_sh = 2LL * pf[3].W * 256; o.x_sn = (long long)pf[3].H * pf[3].W * 256;
     }
-    T4 t = rpn_t; t.H = xin.H; t.W = xin.W;
+    T4 t = scratch; t.H = xin.H; t.W = xin.W;
     b.conv("proposal_generator.rpn_head.conv", xin, t, o);
     rpn_head[l] = b.act(B, xin.H, xin.W, 16, 1);
     Builder::ConvOpt op; op.k = 1;
@@ -333,6 +341,30 @@ int build_plan(dpb200_session* s) {
     ra.lvl[l].head = (const float*)rpn_head[l].p; ra.lvl[l].H = xin.H; ra.lvl[l].W = xin.W;
     ra.lvl[l].stride = (float)(4 << l);
     cell_anchors((float)(32 << l), ra.lvl[l].anchors);
+  };
+  for (int l = 3; l >= 0; --l) {
+    lat[l] = b.act(B, res_out[l].H, res_out[l].W, 256);
+    Builder::ConvOpt o; o.k = 1;
+    if (l < 3) { o.res = &lat[l + 1]; o.res_shift = 1; }
+    b.conv("backbone.fpn_lateral" + std::to_string(l + 2), res_out[l], lat[l], o);
+    pf[l] = b.act(B, res_out[l].H, res_out[l].W, 256);
+    Builder::ConvOpt oo; oo.k = 3; oo.pad = 1;
+    if (l > 0) {
+      const int ev = l == 3 ? EV_LAT5 : l == 2 ? EV_LAT4 : EV_LAT3;
+      b.record(ev);                       // lat[l] is complete (main stream)
+      b.stream = 1;
+      b.wait(ev);
+      b.conv("backbone.fpn_output" + std::to_string(l + 2), lat[l], pf[l], oo);
+      if (l == 1) {                       // p3, p4, p5 exist (side stream order): the small RPN levels follow them
+        for (int r = 1; r < 5; ++r) rpn_level(r, rpn_t_side);
+        b.record(EV_SIDE_FPN);
+      }
+      b.stream = 0;
+    } else {
+      b.conv("backbone.fpn_output" + std::to_string(l + 2), lat[l], pf[l], oo);
+      rpn_level(0, rpn_t);
+    }
+    b.tap("p" + std::to_string(l + 2), pf[l]);
   }
   // ---- a8/a9 proposals
   const int R = cfg.rpn_post_topk, K = cfg.rpn_pre_topk;
@@ -351,6 +383,16 @@ int build_plan(dpb200_session* s) {
   b.tap_raw("rpn_cand_boxes", ra.cand_boxes, B, 5, K, 4, 1);
   b.tap_raw("rpn_cand_scores", ra.cand_scores, B, 5, K, 1, 1);
   b.tap_raw("rpn_cand_keep", ra.cand_keep, B, 5, K, 1, 3);
+  // Proposal selection and the box branch are a chain of small, latency-bound launches; the Panoptic-FPN decoder
+  // only needs the FPN maps. With a decoder the chain stays on the side stream (a parallel branch of the captured graph)
+  // and joins before the DensePose pooler; without one everything returns to the main stream here.
+  if (cfg.decoder_on) {
+    b.record(EV_MAIN_RPN);                // p2 and its RPN head are complete (main stream)
+    b.stream = 1;
+    b.wait(EV_MAIN_RPN);
+  } else {
+    b.wait(EV_SIDE_FPN);
+  }
   b.op([ra](cudaStream_t st) { return launch_rpn_topk_decode(ra, st); }, "rpn_topk_decode");
   b.op([ra](cudaStream_t st) { return launch_rpn_nms(ra, st); }, "rpn_nms");
   b.op([ra](cudaStream_t st) { return launch_rpn_merge(ra, st); }, "rpn_merge");
@@ -407,6 +449,11 @@ int build_plan(dpb200_session* s) {
   }
   b.tap_raw("dp_total", s->dp_total, 1, 1, 1, 1, 2);
   const int* nv = s->dp_total;
+  if (cfg.decoder_on) {
+    b.record(EV_CHAIN);                   // detections, DensePose ROIs and their count exist (side stream)
+    b.stream = 0;
+    b.wait(EV_SIDE_FPN);                  // p3..p5 came from the side stream
+  }
 
   // ---- a14 decoder
   T4 dp_feat[4]; int dp_levels = 4;
@@ -449,6 +496,7 @@ int build_plan(dpb200_session* s) {
     T4 dec = b.act(B, pf[0].H, pf[0].W, 256);
     { Builder::ConvOpt o; o.k = 1; b.conv("roi_heads.decoder.predictor", merged, dec, o); }
     b.tap("decoder", dec);
+    b.wait(EV_CHAIN);
     dp_feat[0] = dec; dp_levels = 1;
   } else {
     for (int l = 0; l < 4; ++l) dp_feat[l] = pf[l];
@@ -620,11 +668,44 @@ static bool same_io(const dpb200_forward_io& a, const dpb200_forward_io& b) {
 }
 
 static int run_ops(dpb200_session* s, cudaStream_t st) {
-  for (auto& f : s->ops) {
-    int r = f(st);
-    if (r) return r;
+  auto cuda_ok = [](cudaError_t e, const char* what) {
+    if (e != cudaSuccess) { set_error("session_run: %s: %s", what, cudaGetErrorString(e)); return false; }
+    return true;
+  };
+  bool side_used = false;
+  auto join = [&]() {                    // the side stream's work so far precedes whatever follows on the main stream
+    if (!side_used) return true;
+    side_used = false;
+    return cuda_ok(cudaEventRecord(s->evs[dpb200_session::kEvents - 1], s->side), "join record") &&
+           cuda_ok(cudaStreamWaitEvent(st, s->evs[dpb200_session::kEvents - 1], 0), "join wait");
+  };
+  int rc = 0;
+  for (const auto& it : s->sched) {
+    if (it.stream == 1 && !s->side) {
+      if (!cuda_ok(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking), "side stream")) return -6;
+    }
+    if (it.kind != 0 && !s->evs[it.idx]) {
+      if (!cuda_ok(cudaEventCreateWithFlags(&s->evs[it.idx], cudaEventDisableTiming), "event")) { rc = -6; break; }
+    }
+    cudaStream_t target = it.stream == 1 ? s->side : st;
+    if (it.kind == 0) {
+      rc = s->ops[it.idx](target);
+      if (rc) break;
+      if (it.stream == 1) side_used = true;
+    } else if (it.kind == 1) {
+      if (!cuda_ok(cudaEventRecord(s->evs[it.idx], target), "event record")) { rc = -6; break; }
+    } else {
+      if (!cuda_ok(cudaStreamWaitEvent(target, s->evs[it.idx], 0), "event wait")) { rc = -6; break; }
+    }
   }
-  return 0;
+  // join unconditionally: a capture must never end (or fail) with the side stream still forked
+  if (s->side) {
+    if (!s->evs[dpb200_session::kEvents - 1] &&
+        !cuda_ok(cudaEventCreateWithFlags(&s->evs[dpb200_session::kEvents - 1], cudaEventDisableTiming), "event")) return -6;
+    side_used = side_used || rc != 0;
+    if (!join() && !rc) rc = -6;
+  }
+  return rc;
 }
 
 int dpb200_session_set_graph(dpb200_session* s, int32_t enable) {
