@@ -244,6 +244,11 @@ typedef struct dpb200_forward_io {
   void* extra[5];           /* [B*dets_per_image, extra_ch[i], 4S, 4S] for the confidence heads the model carries (same
                              * dtype as u / v), or NULL to skip a head                                      */
 } dpb200_forward_io;
+/* Enqueues one forward pass. Everything is ordered after the work already on `stream` and is complete, as far as `stream`
+ * can tell, when the call's last launch has run: internally the launches form a two-branch graph (the proposal / box chain
+ * and the small FPN / RPN levels run on a side stream the session owns, forked from and joined back into `stream` with
+ * events), so the caller only ever synchronises with `stream`. The side stream and its events are created on the first
+ * run; nothing else is allocated. One run at a time per session (use one session per concurrent stream). */
 int dpb200_session_run(dpb200_session* s, const dpb200_forward_io* io, void* stream);
 /* enable != 0: dpb200_session_run captures its launch sequence into a CUDA graph the first time it sees an
  * io binding (all pointers + bgr) and replays the instantiated graph afterwards (one host call instead of
