@@ -680,6 +680,14 @@ static int run_ops(dpb200_session* s, cudaStream_t st) {
            cuda_ok(cudaStreamWaitEvent(st, s->evs[dpb200_session::kEvents - 1], 0), "join wait");
   };
   int rc = 0;
+  // DPB200_SERIAL_SCHEDULE=1: every launch on the caller's stream in list order (the reference the two-stream schedule is
+  // tested against: a missing event edge shows up as a difference, tests/test_gpu_e2e.py)
+  const char* serial_env = getenv("DPB200_SERIAL_SCHEDULE");
+  if (serial_env && serial_env[0] == '1') {
+    for (const auto& it : s->sched)
+      if (it.kind == 0 && (rc = s->ops[it.idx](st)) != 0) return rc;
+    return 0;
+  }
   for (const auto& it : s->sched) {
     if (it.stream == 1 && !s->side) {
       if (!cuda_ok(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking), "side stream")) return -6;

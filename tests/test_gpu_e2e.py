@@ -118,6 +118,39 @@ def test_graph_replay_equals_plain_launches(s1x):
                 assert torch.equal(r[k], s[k]), k
 
 
+@pytest.mark.parametrize("name,batch,size", [("densepose_rcnn_R_50_FPN_s1x", 1, (480, 640)), ("densepose_rcnn_R_50_FPN_s1x", 3, (240, 600)),
+                                             ("densepose_rcnn_R_101_FPN_DL_s1x", 2, (240, 600)),
+                                             ("densepose_rcnn_R_50_FPN_s1x_legacy", 2, (240, 600))])
+def test_two_stream_schedule_equals_the_serial_one(name, batch, size, monkeypatch):
+    """The session runs its launches as a two-branch graph (proposal / box chain and the small FPN / RPN levels on a side
+    stream, explicit event edges, engine.cu run_ops). DPB200_SERIAL_SCHEDULE=1 runs the same launches in list order on one
+    stream: every output and the intermediate maps must be bit-identical, run after run, with plain launches and with the
+    captured graph - a missing edge is a race and shows up here as a difference."""
+    from densepose_torchscript_b200.config import BUILTIN
+    from densepose_torchscript_b200.engine import Engine
+    spec = BUILTIN[name]
+    sd = W.make_state_dict(O.SPECS[name], 0)
+    imgs = torch.stack([W.synthetic_image(size[0], size[1], seed=40 + i) for i in range(batch)])
+    monkeypatch.setenv("DPB200_SERIAL_SCHEDULE", "1")
+    serial = Engine(spec, sd, use_graph=False)
+    ref = [{k: v.clone() for k, v in r.items()} for r in serial.forward_batch(imgs)]
+    sess = serial.session(batch, size[0], size[1], False)
+    taps = {t: sess.tap(t).clone() for t in ("p2", "p3", "p4", "p5", "rpn_head0", "rpn_head3", "rpn_head4", "proposal_boxes")}
+    monkeypatch.delenv("DPB200_SERIAL_SCHEDULE")
+    for use_graph in (False, True):
+        eng = Engine(spec, sd, use_graph=use_graph)
+        for it in range(12):
+            got = eng.forward_batch(imgs)
+            torch.cuda.synchronize()
+            for r, s in zip(got, ref):
+                assert set(r) == set(s)
+                for k in s:
+                    assert torch.equal(r[k], s[k]), (use_graph, it, k)
+        es = eng.session(batch, size[0], size[1], False)
+        for t, v in taps.items():
+            assert torch.equal(es.tap(t), v), (use_graph, t)
+
+
 def test_full_size_properties(s1x):
     """BASELINE-size input (800x1333): shapes, ordering, clipping and the zero-detection path."""
     eng, _ = s1x
