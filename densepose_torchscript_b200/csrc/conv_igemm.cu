@@ -821,7 +821,11 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d, int num_sms) {
   plan->staged = staged ? 1 : 0;
   p.res_tma = (staged && res_matrix) ? 1 : 0;
   p.nslab = 0;
-  if (staged) p.nslab = (p.res_tma && k_iters <= 2) ? 8 : (k_iters > 16 ? 2 : 4);
+  // slab ring of the staged epilogue (same-box sweep over 2 / 3 / 4 / 6 / 8 slabs on the path's shapes, round 2): four
+  // slabs, or two where the shared memory is better spent on pipeline stages - the long-K convs and the narrow 3x3s
+  // (res2's 64->64: one more A stage is worth 14 %). Eight residual-prefetch slabs for the K <= 2 bottleneck outputs
+  // (round 1's choice) lose 5-8 % to four.
+  if (staged) p.nslab = (k_iters > 16 || (k_iters > 8 && block_n <= 128)) ? 2 : 4;
 
   // CTA pairs (cta_group::2): staged im2col convs whose N tile splits into two halves of a multiple of 16 rows.
   // Chosen automatically for the long-K, 256-wide tiles (the 3x3 256->256 / 512->512 convs), where halving the
